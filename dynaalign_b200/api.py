@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's R-facing interface for the all-pairs similarity hot path.
+
+Same names, argument meaning, defaults and error text as the reference:
+
+  similarityMH(sequences, k=4, n_hash=50)                        R/RcppExports.R:15  -> src/minHash.cpp:119
+  similarityNW(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4)
+                                                                 R/RcppExports.R:34  -> src/pairwiseSeqAlign.cpp:331
+  shingle, create_vocab, create_char_matrix, create_hash_parameters, apply_hash,
+  compute_signature_matrix, compute_distance_matrix, minhash     R/minHash.R
+
+R is not available in the build image, so this Python layer plays the role of the R stubs: it marshals the
+character vector into the flat (residues, offsets) form and calls the C ABI through ctypes -- exactly what the
+Rcpp shims in rpkg/src do.  All numeric work happens in the CUDA library; nothing here computes a similarity.
+Results are column-major (Fortran-order) float64 n x n arrays, symmetric, like the reference's NumericMatrix;
+``dimnames`` ("1".."n") are returned by :func:`dimnames`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import DynaAlignError, check, flatten, lib, ptr
+
+__all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
+           "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
+           "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
+           "substitution_matrix", "DynaAlignError"]
+
+
+def dimnames(n):
+    """list(as.character(1:n), as.character(1:n)) -- what both reference functions attach (src/minHash.cpp:181-185)."""
+    labels = [str(i + 1) for i in range(n)]
+    return [labels, list(labels)]
+
+
+def hashfamily_seeds(seed, n_hash):
+    """HashFamily(n_hash, seed) seed vector (src/minHash.cpp:73-80)."""
+    out = np.zeros(max(int(n_hash), 1), dtype=np.uint32)
+    check(lib().dyna_hashfamily_seeds(C.c_uint32(seed), int(n_hash), ptr(out, C.c_uint32)))
+    return out[:n_hash]
+
+
+def similarityMH(sequences, k=4, n_hash=50, *, seed=None, seeds=None, n_gpus=1):
+    """Drop-in for the reference's similarityMH.  ``seed``/``seeds`` inject the HashFamily seed (tests);
+    by default the seed comes from std::random_device, as in the reference."""
+    sequences = list(sequences)
+    n = len(sequences)
+    res, off = flatten(sequences)
+    if seeds is None and seed is not None and n_hash > 0:
+        seeds = hashfamily_seeds(seed, n_hash)
+    sp = None
+    if seeds is not None:
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        sp = ptr(seeds, C.c_uint32)
+    out = np.zeros((n, n), dtype=np.float64, order="F")
+    check(lib().dyna_similarityMH(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, int(k), int(n_hash), sp,
+                                  ptr(out, C.c_double), int(n_gpus)))
+    return out
+
+
+def similarityNW(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, *, n_gpus=1):
+    """Drop-in for the reference's similarityNW (identity = matches / alignment length of the NW traceback)."""
+    sequences = list(sequences)
+    n = len(sequences)
+    res, off = flatten(sequences)
+    out = np.zeros((n, n), dtype=np.float64, order="F")
+    check(lib().dyna_similarityNW(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, matrixName.encode(), int(gapOpen),
+                                  int(gapExt), ptr(out, C.c_double), int(n_gpus)))
+    return out
+
+
+# ----------------------------------------------------------------------------- pieces of the C++ path
+def mh_signatures(sequences, k, seeds):
+    sequences = list(sequences)
+    res, off = flatten(sequences)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    out = np.zeros((len(sequences), len(seeds)), dtype=np.uint32)
+    check(lib().dyna_mh_signatures_murmur3(ptr(res, C.c_uint8), ptr(off, C.c_int64), len(sequences), int(k),
+                                           ptr(seeds, C.c_uint32), len(seeds), ptr(out, C.c_uint32)))
+    return out
+
+
+def tri_strict_size(n, row_begin=0, row_end=None):
+    row_end = n if row_end is None else row_end
+    f = lambda r: r * n - r * (r + 1) // 2
+    return f(row_end) - f(row_begin)
+
+
+def tri_diag_size(n, row_begin=0, row_end=None):
+    row_end = n if row_end is None else row_end
+    f = lambda r: r * n - r * (r - 1) // 2
+    return f(row_end) - f(row_begin)
+
+
+def mh_match_counts(sig, row_begin=0, row_end=None):
+    sig = np.ascontiguousarray(sig, dtype=np.uint32)
+    n, n_hash = sig.shape
+    row_end = n if row_end is None else row_end
+    sz = tri_strict_size(n, row_begin, row_end)
+    out = np.zeros(max(sz, 1), dtype=np.uint16)
+    check(lib().dyna_mh_match_counts(ptr(sig, C.c_uint32), n, n_hash, row_begin, row_end, ptr(out, C.c_uint16)))
+    return out[:sz]
+
+
+def nw_pair_stats(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, row_begin=0, row_end=None):
+    sequences = list(sequences)
+    n = len(sequences)
+    row_end = n if row_end is None else row_end
+    res, off = flatten(sequences)
+    sz = tri_diag_size(n, row_begin, row_end)
+    mt = np.zeros(max(sz, 1), dtype=np.uint32)
+    ln = np.zeros(max(sz, 1), dtype=np.uint32)
+    check(lib().dyna_nw_pair_stats(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, matrixName.encode(), int(gapOpen),
+                                   int(gapExt), row_begin, row_end, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32)))
+    return mt[:sz], ln[:sz]
+
+
+def partition_rows(n, nshards, weights=None, include_diagonal=False):
+    out = np.zeros(nshards + 1, dtype=np.int64)
+    wp = None
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.int64)
+        wp = ptr(weights, C.c_int64)
+    check(lib().dyna_partition_rows(n, wp, 1 if include_diagonal else 0, nshards, ptr(out, C.c_int64)))
+    return out
+
+
+def substitution_matrix(name):
+    out = np.zeros((24, 24), dtype=np.int8)
+    check(lib().dyna_substitution_matrix(name.encode(), ptr(out, C.c_int8)))
+    return out
+
+
+# ----------------------------------------------------------------------------- R pipeline (R/minHash.R)
+class RError(DynaAlignError):
+    def __init__(self, message):
+        super().__init__(L.ERR_INVALID, message)
+
+
+def shingle(x, k):
+    """R/minHash.R:12-23 (host string handling, as in R)."""
+    if not isinstance(x, str):
+        raise RError("Input 'x' must be a single character string")
+    if isinstance(k, bool) or not isinstance(k, (int, float, np.integer, np.floating)) or k < 1 or k > len(x):
+        raise RError("'k' must be a positive integer between 1 and %d" % len(x))
+    k = int(k)
+    return [x[i:i + k] for i in range(len(x) - k + 1)]
+
+
+def create_vocab(sequences, k):
+    """R/minHash.R:38-41: sort(unique(all shingles)); byte order (== R's collation for upper-case ASCII)."""
+    seen = set()
+    for s in sequences:
+        seen.update(shingle(s, k))
+    return sorted(seen)
+
+
+def create_char_matrix(sequences, vocab, k):
+    """R/minHash.R:60-66: V x N integer 0/1 matrix."""
+    pos = {v: i for i, v in enumerate(vocab)}
+    m = np.zeros((len(vocab), len(sequences)), dtype=np.int32)
+    for j, s in enumerate(sequences):
+        for sh in shingle(s, k):
+            i = pos.get(sh)
+            if i is not None:
+                m[i, j] = 1
+    return m
+
+
+def create_hash_parameters(n_hash, max_val, rng=None):
+    """R/minHash.R:81-88.  R's sample() stream cannot be reproduced outside R; ranges and lengths follow the source."""
+    if n_hash < 1:
+        raise RError("Number of hash functions must be positive")
+    if max_val < 2:
+        raise RError("Maximum value must be at least 2")
+    rng = np.random.default_rng() if rng is None else rng
+    return {"a": rng.integers(1, max_val + 1, size=n_hash, dtype=np.int64),
+            "b": rng.integers(0, max_val + 1, size=n_hash, dtype=np.int64)}
+
+
+def apply_hash(x, a, b, m):
+    """R/minHash.R:104-106."""
+    return (np.asarray(a) * np.asarray(x) + np.asarray(b)) % m
+
+
+def compute_signature_matrix(char_matrix, hash_params, max_val):
+    """R/minHash.R:126-143 on the GPU: n_hash x n_docs double matrix (Inf where a document has no shingle)."""
+    char_matrix = np.asarray(char_matrix)
+    a = np.ascontiguousarray(hash_params["a"], dtype=np.int64)
+    b = np.ascontiguousarray(hash_params["b"], dtype=np.int64)
+    n_docs = char_matrix.shape[1]
+    rows, docs = np.nonzero(char_matrix.T == 1)[::-1]  # per document, ascending rank
+    order = np.lexsort((rows, docs))
+    ranks = (rows[order] + 1).astype(np.int32)
+    counts = np.bincount(docs, minlength=n_docs)
+    roff = np.zeros(n_docs + 1, dtype=np.int64)
+    np.cumsum(counts, out=roff[1:])
+    if ranks.size == 0:
+        ranks = np.ones(1, dtype=np.int32)
+    sig = np.zeros((n_docs, len(a)), dtype=np.uint32)
+    check(lib().dyna_mh_signatures_linear(ptr(ranks, C.c_int32), ptr(roff, C.c_int64), n_docs, ptr(a, C.c_int64),
+                                          ptr(b, C.c_int64), int(max_val), len(a), ptr(sig, C.c_uint32)))
+    out = sig.T.astype(np.float64)
+    out[sig.T == np.uint32(0xFFFFFFFF)] = np.inf
+    return out
+
+
+def compute_distance_matrix(sig_matrix):
+    """R/minHash.R:166-182 on the GPU.  Arbitrary doubles are relabelled per hash row to dense integer codes
+    (equality-preserving), then the match-count kernel runs with the R distance table."""
+    sig_matrix = np.asarray(sig_matrix, dtype=np.float64)
+    if np.isnan(sig_matrix).any():
+        raise RError("NA/NaN in signature matrix")
+    n_hash, n_docs = sig_matrix.shape
+    codes = np.empty((n_docs, n_hash), dtype=np.uint32)
+    for h in range(n_hash):
+        codes[:, h] = np.unique(sig_matrix[h], return_inverse=True)[1].astype(np.uint32)
+    out = np.zeros((n_docs, n_docs), dtype=np.float64, order="F")
+    check(lib().dyna_mh_match_matrix(ptr(codes, C.c_uint32), n_docs, n_hash, L.MH_DISTANCE, ptr(out, C.c_double), 1))
+    return out
+
+
+def minhash(sequences, k, n_hash, rng=None, hash_params=None):
+    """R/minHash.R:206-221."""
+    sequences = list(sequences)
+    vocab = create_vocab(sequences, k)
+    char_matrix = create_char_matrix(sequences, vocab, k)
+    max_val = len(vocab)
+    if hash_params is None:
+        hash_params = create_hash_parameters(n_hash, max_val, rng)
+    sig_matrix = compute_signature_matrix(char_matrix, hash_params, max_val)
+    dist_matrix = compute_distance_matrix(sig_matrix)
+    return {"vocabulary": vocab, "char_matrix": char_matrix, "sig_matrix": sig_matrix, "dist_matrix": dist_matrix}

@@ -1,0 +1,773 @@
+// extern "C" entry points of libdynaalign_b200 (see include/dynaalign_b200.h) and the host-side driver logic that
+// replaces the reference's loops: input validation with the reference's error strings, HashFamily seed stream,
+// residue encoding, work partitioning (row blocks of the upper triangle), device plans, result expansion.
+// There is no CPU compute path in this file: every similarity value is produced by the kernels in
+// mh_kernels.cu / nw_kernels.cu, and a missing or failing CUDA device is an error.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "blosum_tables.h"
+#include "common.cuh"
+#include "mh_kernels.cuh"
+#include "nw_kernels.cuh"
+
+using namespace dyna;
+
+namespace {
+
+thread_local int g_device = 0;
+
+int use_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: no usable CUDA device (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: device %d out of range (0..%d)", device, count - 1);
+  DYNA_CUDA(cudaSetDevice(device));
+  return DYNA_OK;
+}
+
+int resolve_gpus(int n_gpus, int* out) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: no usable CUDA device (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  *out = (n_gpus <= 0 || n_gpus > count) ? count : n_gpus;
+  return DYNA_OK;
+}
+
+// ---- substitution tables: expand the packed lower triangles once
+struct Tables {
+  int8_t full[kNumTables][576];
+  int8_t aa[256];
+  Tables() {
+    for (int t = 0; t < kNumTables; ++t)
+      for (int i = 0; i < 24; ++i)
+        for (int j = 0; j < 24; ++j) {
+          const int hi = std::max(i, j), lo = std::min(i, j);
+          full[t][i * 24 + j] = kTableTri[t][hi * (hi + 1) / 2 + lo];
+        }
+    for (int c = 0; c < 256; ++c) aa[c] = -1;
+    for (int i = 0; i < 24; ++i) aa[(unsigned char)kAlphabet[i]] = (int8_t)i;
+  }
+};
+const Tables& tables() {
+  static const Tables t;
+  return t;
+}
+int find_table(const char* name) {
+  for (int t = 0; t < kNumTables; ++t)
+    if (strcmp(name, kTableNames[t]) == 0) return t;
+  return -1;
+}
+
+// first residue error in the order the reference discovers it (src/pairwiseSeqAlign.cpp:239-250 inside the
+// i-major / j>=i pair loop :340-346): rows that are empty validate nothing; the first non-empty sequence i0 is
+// checked as sequence1 at its first residue, then as sequence2 (pair (i0,i0)); every later sequence is checked as
+// sequence2 against i0.  Returns DYNA_OK or the reference's message.
+int validate_residues(const uint8_t* res, const int64_t* off, int64_t n) {
+  const int8_t* aa = tables().aa;
+  int64_t i0 = 0;
+  while (i0 < n && off[i0 + 1] == off[i0]) ++i0;
+  if (i0 >= n) return DYNA_OK;
+  const uint8_t* s = res + off[i0];
+  const int64_t L = off[i0 + 1] - off[i0];
+  if (aa[s[0]] < 0) return fail(DYNA_ERR_INVALID, "Invalid amino acid in sequence1: %c", (char)s[0]);
+  for (int64_t p = 0; p < L; ++p)
+    if (aa[s[p]] < 0) return fail(DYNA_ERR_INVALID, "Invalid amino acid in sequence2: %c", (char)s[p]);
+  for (int64_t j = i0 + 1; j < n; ++j)
+    for (int64_t p = off[j]; p < off[j + 1]; ++p)
+      if (aa[res[p]] < 0) return fail(DYNA_ERR_INVALID, "Invalid amino acid in sequence2: %c", (char)res[p]);
+  return DYNA_OK;
+}
+
+// std::mt19937 stream exactly as HashFamily draws it (src/minHash.cpp:73-80)
+void hashfamily_seeds(uint32_t seed, int n_hash, uint32_t* out) {
+  std::mt19937 gen(seed);
+  std::uniform_int_distribution<uint32_t> dis;
+  for (int i = 0; i < n_hash; ++i) out[i] = dis(gen);
+}
+
+int check_mh_args(int64_t n, int k, int n_hash) {
+  // reference messages and order: src/minHash.cpp:121-131
+  if (n == 0) return fail(DYNA_ERR_INVALID, "Input sequences vector cannot be empty");
+  if (k <= 0) return fail(DYNA_ERR_INVALID, "'k' must be a positive integer");
+  if (n_hash <= 0) return fail(DYNA_ERR_INVALID, "Number of hash functions must be positive");
+  if (n_hash > 65535) return fail(DYNA_ERR_UNSUPPORTED, "n_hash > 65535 is not supported (match counts are 16-bit)");
+  if (k > 4096) return fail(DYNA_ERR_UNSUPPORTED, "k > 4096 is not supported");
+  return DYNA_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// MinHash plan
+// =====================================================================================================
+struct dyna_mh_plan {
+  int device = 0;
+  int64_t n = 0;
+  int n_hash = 0, hrows = 0;
+  int64_t npitch = 0, row_begin = 0, row_end = 0, pairs = 0;
+  int k = 0;
+  int64_t max_len = 0;
+  int launches = 0;
+  DevBuf<uint8_t> res;
+  DevBuf<int64_t> off;
+  DevBuf<uint32_t> seeds, sig, sigT, sigTneg;
+  DevBuf<uint16_t> counts;
+  bool have_sequences = false, have_sig = false, have_sigT = false;
+};
+
+extern "C" dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_begin, int64_t row_end, int device) {
+  if (n <= 0 || n_hash <= 0 || n_hash > 65535 || row_begin < 0 || row_end > n || row_begin > row_end) {
+    fail(DYNA_ERR_INVALID, "dyna_mh_plan_create: bad arguments");
+    return nullptr;
+  }
+  if (use_device(device) != DYNA_OK) return nullptr;
+  std::unique_ptr<dyna_mh_plan> p(new dyna_mh_plan);
+  p->device = device;
+  p->n = n;
+  p->n_hash = n_hash;
+  p->hrows = mh_hrows(n_hash);
+  p->npitch = mh_npitch(n);
+  p->row_begin = row_begin;
+  p->row_end = row_end;
+  p->pairs = tri_strict_rows(n, row_end) - tri_strict_rows(n, row_begin);
+  if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch) ||
+      p->sigTneg.alloc((size_t)p->hrows * p->npitch) || p->counts.alloc((size_t)p->pairs))
+    return nullptr;
+  return p.release();
+}
+
+extern "C" int dyna_mh_plan_upload_sequences(dyna_mh_plan* p, const uint8_t* residues, const int64_t* offsets, int k,
+                                             const uint32_t* seeds, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  if (k <= 0) return fail(DYNA_ERR_INVALID, "'k' must be a positive integer");
+  if (k > 4096) return fail(DYNA_ERR_UNSUPPORTED, "k > 4096 is not supported");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = offsets[p->n];
+  p->max_len = 0;
+  for (int64_t i = 0; i < p->n; ++i) p->max_len = std::max(p->max_len, offsets[i + 1] - offsets[i]);
+  DYNA_TRY(p->res.alloc((size_t)total + 8));
+  DYNA_TRY(p->off.alloc((size_t)p->n + 1));
+  DYNA_TRY(p->seeds.alloc((size_t)p->n_hash));
+  DYNA_CUDA(cudaMemcpyAsync(p->res.p, residues, (size_t)total, cudaMemcpyHostToDevice, st));
+  DYNA_CUDA(cudaMemcpyAsync(p->off.p, offsets, sizeof(int64_t) * (size_t)(p->n + 1), cudaMemcpyHostToDevice, st));
+  DYNA_CUDA(cudaMemcpyAsync(p->seeds.p, seeds, sizeof(uint32_t) * (size_t)p->n_hash, cudaMemcpyHostToDevice, st));
+  p->k = k;
+  p->have_sequences = true;
+  p->have_sig = p->have_sigT = false;
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_plan_upload_signatures(dyna_mh_plan* p, const uint32_t* sig, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DYNA_CUDA(cudaMemcpyAsync(p->sig.p, sig, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyHostToDevice, st));
+  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->sigTneg.p, p->npitch, p->hrows, st));
+  p->have_sig = p->have_sigT = true;
+  p->launches = 1;
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_plan_run_signatures(dyna_mh_plan* p, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (!p->have_sequences) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_signatures: no sequences uploaded");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
+  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->sigTneg.p, p->npitch, p->hrows, st));
+  p->have_sig = p->have_sigT = true;
+  p->launches = 2;
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (!p->have_sigT) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match: no signatures on the device");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int l = 0;
+  DYNA_TRY(launch_mh_match(p->sigT.p, p->sigTneg.p, p->npitch, p->hrows, p->n, p->row_begin, p->row_end, p->counts.p, st, &l));
+  p->launches = l;
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_plan_fetch_signatures(dyna_mh_plan* p, uint32_t* sig_out, void* stream) {
+  if (!p || !p->have_sig) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_fetch_signatures: nothing to fetch");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DYNA_CUDA(cudaMemcpyAsync(sig_out, p->sig.p, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_plan_fetch_counts(dyna_mh_plan* p, uint16_t* counts_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->pairs > 0)
+    DYNA_CUDA(cudaMemcpyAsync(counts_out, p->counts.p, sizeof(uint16_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
+extern "C" int64_t dyna_mh_plan_pairs(const dyna_mh_plan* p) { return p ? p->pairs : 0; }
+extern "C" int dyna_mh_plan_launches(const dyna_mh_plan* p) { return p ? p->launches : 0; }
+extern "C" void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan* p) { return p ? p->counts.p : nullptr; }
+extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  delete p;
+}
+
+// =====================================================================================================
+// NW plan
+// =====================================================================================================
+struct NwClass {
+  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp kernel multipass
+  int R;
+  std::vector<NwUnit> units;
+  DevBuf<NwUnit> d_units;
+};
+
+struct dyna_nw_plan {
+  int device = 0;
+  int64_t n = 0, row_begin = 0, row_end = 0, pairs = 0, cells = 0;
+  int gap_open = 0, gap_ext = 0;
+  bool slant = false;
+  int launches = 0;
+  int max_cols = 0;
+  std::vector<std::unique_ptr<NwClass>> classes;
+  DevBuf<uint8_t> codes;
+  DevBuf<int32_t> off;
+  DevBuf<int8_t> sub;
+  DevBuf<uint32_t> matches, length;
+  DevBuf<int32_t> scratch;
+};
+
+extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int64_t* offsets, int64_t n,
+                                             const char* matrix_name, int gap_open, int gap_ext, int64_t row_begin,
+                                             int64_t row_end, int device) {
+  // argument checks in the reference's order: substitution matrix name first (src/pairwiseSeqAlign.cpp:338), then
+  // residues as the pair loop meets them
+  const int t = matrix_name ? find_table(matrix_name) : -1;
+  if (t < 0) {
+    fail(DYNA_ERR_INVALID, "Invalid substitution matrix name: %s", matrix_name ? matrix_name : "(null)");
+    return nullptr;
+  }
+  if (n < 0 || row_begin < 0 || row_end > n || row_begin > row_end) {
+    fail(DYNA_ERR_INVALID, "dyna_nw_plan_create: bad row range");
+    return nullptr;
+  }
+  if (validate_residues(residues, offsets, n) != DYNA_OK) return nullptr;
+  const int64_t total = n ? offsets[n] : 0;
+  if (total >= (1ll << 31)) {
+    fail(DYNA_ERR_UNSUPPORTED, "more than 2^31 residues in one call is not supported");
+    return nullptr;
+  }
+  int64_t max_len = 0;
+  for (int64_t i = 0; i < n; ++i) max_len = std::max(max_len, offsets[i + 1] - offsets[i]);
+  if (max_len > 65535) {
+    fail(DYNA_ERR_UNSUPPORTED, "sequences longer than 65535 residues are not supported");
+    return nullptr;
+  }
+  // int32 head-room: every DP value (plus the slant) must stay far from INT_MIN/2 and INT_MAX
+  const double mag = std::fabs((double)gap_open) + 2.0 * (double)max_len * (std::fabs((double)gap_ext) * 2.0 + 20.0);
+  if (mag > 2.5e8) {
+    fail(DYNA_ERR_UNSUPPORTED, "gap penalties / sequence lengths exceed the exact int32 range of the DP");
+    return nullptr;
+  }
+  if (use_device(device) != DYNA_OK) return nullptr;
+
+  std::unique_ptr<dyna_nw_plan> p(new dyna_nw_plan);
+  p->device = device;
+  p->n = n;
+  p->row_begin = row_begin;
+  p->row_end = row_end;
+  p->gap_open = gap_open;
+  p->gap_ext = gap_ext;
+  p->pairs = tri_diag_rows(n, row_end) - tri_diag_rows(n, row_begin);
+  p->max_cols = (int)std::max<int64_t>(max_len, 1);
+  // slanted recurrence needs score + 2*ge to fit the profile's int8 score byte
+  int smin = 127, smax = -128;
+  for (int i = 0; i < 576; ++i) {
+    smin = std::min<int>(smin, tables().full[t][i]);
+    smax = std::max<int>(smax, tables().full[t][i]);
+  }
+  p->slant = (smin + 2 * (int64_t)gap_ext >= -128) && (smax + 2 * (int64_t)gap_ext <= 127);
+  if (const char* e = getenv("DYNA_NW_SLANT")) p->slant = p->slant && (atoi(e) != 0);
+
+  // encode residues, 32-bit offsets
+  std::vector<uint8_t> codes((size_t)total + 4);
+  std::vector<int32_t> off32((size_t)n + 1);
+  const int8_t* aa = tables().aa;
+  for (int64_t q = 0; q < total; ++q) codes[(size_t)q] = (uint8_t)aa[residues[q]];
+  for (int64_t i = 0; i <= n; ++i) off32[(size_t)i] = (int32_t)(n ? offsets[i] : 0);
+
+  // suffix sums of lengths -> exact cell count of the row range
+  {
+    std::vector<int64_t> suffix((size_t)n + 1, 0);
+    for (int64_t i = n - 1; i >= 0; --i) suffix[(size_t)i] = suffix[(size_t)i + 1] + (offsets[i + 1] - offsets[i]);
+    int64_t cells = 0;
+    for (int64_t i = row_begin; i < row_end; ++i) cells += (offsets[i + 1] - offsets[i]) * suffix[(size_t)i];
+    p->cells = cells;
+  }
+
+  // work units per kernel class
+  std::map<std::pair<int, int>, NwClass*> by_key;
+  auto get_class = [&](int kind, int R) -> NwClass* {
+    auto key = std::make_pair(kind, R);
+    auto it = by_key.find(key);
+    if (it != by_key.end()) return it->second;
+    p->classes.emplace_back(new NwClass);
+    NwClass* c = p->classes.back().get();
+    c->kind = kind;
+    c->R = R;
+    by_key[key] = c;
+    return c;
+  };
+  bool need_scratch = false;
+  for (int64_t i = row_begin; i < row_end; ++i) {
+    const int m = (int)(offsets[i + 1] - offsets[i]);
+    int kind, R, step;
+    if (m == 0) { kind = 0; R = 0; step = 4096; }
+    else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
+    else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
+    else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
+    NwClass* c = get_class(kind, R);
+    for (int64_t j = i; j < n; j += step)
+      c->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)std::min<int64_t>(step, n - j)});
+  }
+
+  if (p->codes.alloc(codes.size()) || p->off.alloc(off32.size()) || p->sub.alloc(576) ||
+      p->matches.alloc((size_t)p->pairs) || p->length.alloc((size_t)p->pairs))
+    return nullptr;
+  if (need_scratch && p->scratch.alloc((size_t)kNwMultiPassGrid * 8 * 3 * (size_t)p->max_cols)) return nullptr;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  bool ok = cp(p->codes.p, codes.data(), codes.size()) && cp(p->off.p, off32.data(), off32.size() * sizeof(int32_t)) &&
+            cp(p->sub.p, tables().full[t], 576);
+  for (auto& c : p->classes) {
+    if (c->d_units.alloc(c->units.size())) return nullptr;
+    ok = ok && cp(c->d_units.p, c->units.data(), c->units.size() * sizeof(NwUnit));
+  }
+  if (!ok) {
+    fail(DYNA_ERR_CUDA, "DynaAlign CUDA: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p.release();
+}
+
+extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NwDeviceData d;
+  d.codes = p->codes.p;
+  d.off = p->off.p;
+  d.sub = p->sub.p;
+  d.n = p->n;
+  d.slab_base = tri_diag_rows(p->n, p->row_begin);
+  d.matches = p->matches.p;
+  d.length = p->length.p;
+  d.gap_open = p->gap_open;
+  d.gap_ext = p->gap_ext;
+  d.one = 1u;
+  p->launches = 0;
+  for (auto& c : p->classes) {
+    const int nu = (int)c->units.size();
+    if (nu == 0) continue;
+    switch (c->kind) {
+      case 0: DYNA_TRY(launch_nw_empty_rows(d, c->d_units.p, nu, st)); break;
+      case 1: DYNA_TRY(launch_nw_thread(c->R, p->slant, d, c->d_units.p, nu, st)); break;
+      case 2: DYNA_TRY(launch_nw_warp(c->R, p->slant, false, d, c->d_units.p, nu, nullptr, 0, st)); break;
+      default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, st)); break;
+    }
+    ++p->launches;
+  }
+  return DYNA_OK;
+}
+
+extern "C" int dyna_nw_plan_fetch(dyna_nw_plan* p, uint32_t* matches_out, uint32_t* length_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->pairs > 0) {
+    DYNA_CUDA(cudaMemcpyAsync(matches_out, p->matches.p, sizeof(uint32_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaMemcpyAsync(length_out, p->length.p, sizeof(uint32_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
+  }
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
+extern "C" int64_t dyna_nw_plan_pairs(const dyna_nw_plan* p) { return p ? p->pairs : 0; }
+extern "C" int64_t dyna_nw_plan_cells(const dyna_nw_plan* p) { return p ? p->cells : 0; }
+extern "C" int dyna_nw_plan_launches(const dyna_nw_plan* p) { return p ? p->launches : 0; }
+extern "C" void dyna_nw_plan_destroy(dyna_nw_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  delete p;
+}
+
+// =====================================================================================================
+// misc
+// =====================================================================================================
+extern "C" const char* dyna_last_error(void) { return err_slot().c_str(); }
+extern "C" int dyna_version(void) { return 100; }
+extern "C" int dyna_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+extern "C" int dyna_set_device(int device) {
+  DYNA_TRY(use_device(device));
+  g_device = device;
+  return DYNA_OK;
+}
+
+extern "C" int dyna_partition_rows(int64_t n, const int64_t* weights, int include_diagonal, int nshards,
+                                   int64_t* bounds_out) {
+  if (n < 0 || nshards <= 0 || !bounds_out) return fail(DYNA_ERR_INVALID, "dyna_partition_rows: bad arguments");
+  // work of row i = w_i * sum_{j >= i (or > i)} w_j ; cut the prefix sums at equal shares
+  std::vector<long double> rowwork((size_t)n);
+  long double suffix = 0, total = 0;
+  for (int64_t i = n - 1; i >= 0; --i) {
+    const long double wi = weights ? (long double)weights[i] : 1.0L;
+    const long double others = include_diagonal ? suffix + wi : suffix;
+    rowwork[(size_t)i] = wi * others + 1e-9L;  // epsilon keeps zero-work rows ordered
+    suffix += wi;
+  }
+  for (int64_t i = 0; i < n; ++i) total += rowwork[(size_t)i];
+  bounds_out[0] = 0;
+  long double acc = 0;
+  int64_t i = 0;
+  for (int s = 1; s < nshards; ++s) {
+    const long double target = total * (long double)s / (long double)nshards;
+    while (i < n && acc + rowwork[(size_t)i] * 0.5L < target) acc += rowwork[(size_t)i++];
+    bounds_out[s] = i;
+  }
+  bounds_out[nshards] = n;
+  return DYNA_OK;
+}
+
+extern "C" int dyna_hashfamily_seeds(uint32_t seed, int n_hash, uint32_t* seeds_out) {
+  if (n_hash <= 0) return fail(DYNA_ERR_INVALID, "Number of hash functions must be positive");
+  hashfamily_seeds(seed, n_hash, seeds_out);
+  return DYNA_OK;
+}
+extern "C" uint32_t dyna_random_seed(void) { return std::random_device{}(); }
+
+extern "C" int dyna_substitution_matrix(const char* name, int8_t* out576) {
+  const int t = name ? find_table(name) : -1;
+  if (t < 0) return fail(DYNA_ERR_INVALID, "Invalid substitution matrix name: %s", name ? name : "(null)");
+  memcpy(out576, tables().full[t], 576);
+  return DYNA_OK;
+}
+extern "C" void dyna_aa_index_table(int8_t* out256) { memcpy(out256, tables().aa, 256); }
+
+// =====================================================================================================
+// MinHash host entry points
+// =====================================================================================================
+extern "C" int dyna_mh_signatures_murmur3(const uint8_t* residues, const int64_t* offsets, int64_t n, int k,
+                                          const uint32_t* seeds, int n_hash, uint32_t* sig_out) {
+  DYNA_TRY(check_mh_args(n, k, n_hash));
+  dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, 0, g_device);
+  if (!p) return DYNA_ERR_CUDA;
+  int rc = dyna_mh_plan_upload_sequences(p, residues, offsets, k, seeds, nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_run_signatures(p, nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_fetch_signatures(p, sig_out, nullptr);
+  dyna_mh_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int dyna_mh_signatures_linear(const int32_t* ranks, const int64_t* rank_offsets, int64_t n, const int64_t* a,
+                                         const int64_t* b, int64_t m, int n_hash, uint32_t* sig_out) {
+  if (n <= 0) return fail(DYNA_ERR_INVALID, "Input sequences vector cannot be empty");
+  if (n_hash < 1) return fail(DYNA_ERR_INVALID, "Number of hash functions must be positive");  // R/minHash.R:82
+  if (m < 2) return fail(DYNA_ERR_INVALID, "Maximum value must be at least 2");                 // R/minHash.R:83
+  if (m >= (1ll << 31)) return fail(DYNA_ERR_UNSUPPORTED, "vocabulary larger than 2^31-1 is not supported");
+  for (int h = 0; h < n_hash; ++h)
+    if (a[h] < 0 || b[h] < 0 || a[h] >= (1ll << 31) || b[h] >= (1ll << 31))
+      return fail(DYNA_ERR_UNSUPPORTED, "hash parameters must be in [0, 2^31)");
+  DYNA_TRY(use_device(g_device));
+  const int64_t total = rank_offsets[n];
+  for (int64_t q = 0; q < total; ++q)
+    if (ranks[q] < 1) return fail(DYNA_ERR_INVALID, "vocabulary ranks are 1-based");
+  DevBuf<int32_t> d_ranks;
+  DevBuf<int64_t> d_roff, d_a, d_b;
+  DevBuf<uint32_t> d_sig;
+  DYNA_TRY(d_ranks.alloc((size_t)total));
+  DYNA_TRY(d_roff.alloc((size_t)n + 1));
+  DYNA_TRY(d_a.alloc((size_t)n_hash));
+  DYNA_TRY(d_b.alloc((size_t)n_hash));
+  DYNA_TRY(d_sig.alloc((size_t)n * n_hash));
+  DYNA_CUDA(cudaMemcpy(d_ranks.p, ranks, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice));
+  DYNA_CUDA(cudaMemcpy(d_roff.p, rank_offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice));
+  DYNA_CUDA(cudaMemcpy(d_a.p, a, sizeof(int64_t) * (size_t)n_hash, cudaMemcpyHostToDevice));
+  DYNA_CUDA(cudaMemcpy(d_b.p, b, sizeof(int64_t) * (size_t)n_hash, cudaMemcpyHostToDevice));
+  DYNA_TRY(launch_mh_signature_linear(d_ranks.p, d_roff.p, n, d_a.p, d_b.p, m, n_hash, d_sig.p, nullptr));
+  DYNA_CUDA(cudaMemcpy(sig_out, d_sig.p, sizeof(uint32_t) * (size_t)n * n_hash, cudaMemcpyDeviceToHost));
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_match_counts(const uint32_t* sig, int64_t n, int n_hash, int64_t row_begin, int64_t row_end,
+                                    uint16_t* counts_tri_out) {
+  if (n <= 0) return fail(DYNA_ERR_INVALID, "Input sequences vector cannot be empty");
+  if (n_hash <= 0) return fail(DYNA_ERR_INVALID, "Number of hash functions must be positive");
+  if (n_hash > 65535) return fail(DYNA_ERR_UNSUPPORTED, "n_hash > 65535 is not supported (match counts are 16-bit)");
+  dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, row_begin, row_end, g_device);
+  if (!p) return err_slot().empty() ? DYNA_ERR_CUDA : (err_slot().find("CUDA") != std::string::npos ? DYNA_ERR_CUDA : DYNA_ERR_INVALID);
+  int rc = dyna_mh_plan_upload_signatures(p, sig, nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_run_match(p, nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_fetch_counts(p, counts_tri_out, nullptr);
+  dyna_mh_plan_destroy(p);
+  return rc;
+}
+
+namespace {
+
+// value table for the expansion: reference arithmetic per kind
+void mh_value_table(int n_hash, int kind, std::vector<double>& table, double* diag) {
+  table.resize((size_t)n_hash + 1);
+  for (int c = 0; c <= n_hash; ++c) {
+    if (kind == DYNA_MH_DISTANCE) {
+      // R: 1 - mean(logical): long double accumulate and divide, then double (R/minHash.R:174-175)
+      const double sim = (double)((long double)c / (long double)n_hash);
+      table[(size_t)c] = 1.0 - sim;
+    } else {
+      table[(size_t)c] = static_cast<double>(c) / n_hash;  // src/minHash.cpp:174
+    }
+  }
+  *diag = (kind == DYNA_MH_DISTANCE) ? 0.0 : 1.0;
+}
+
+// host-side scatter of a counts slab (used when several GPUs each own a row block)
+void mh_expand_host(const uint16_t* counts, int64_t n, int64_t row_begin, int64_t row_end, const std::vector<double>& table,
+                    double diag, double* out) {
+  const int64_t base = tri_strict_rows(n, row_begin);
+  for (int64_t i = row_begin; i < row_end; ++i) {
+    out[i + i * n] = diag;
+    const uint16_t* row = counts + (tri_strict_rows(n, i) - base) - (i + 1);
+    for (int64_t j = i + 1; j < n; ++j) {
+      const double v = table[row[j]];
+      out[i + j * n] = v;
+      out[j + i * n] = v;
+    }
+  }
+}
+
+// one GPU: plan over all rows with signatures already resident -> expanded matrix to host
+int mh_matrix_single(dyna_mh_plan* p, int kind, double* out) {
+  std::vector<double> table;
+  double diag;
+  mh_value_table(p->n_hash, kind, table, &diag);
+  DevBuf<double> d_table, d_out;
+  DYNA_TRY(d_table.alloc(table.size()));
+  DYNA_TRY(d_out.alloc((size_t)p->n * p->n));
+  DYNA_CUDA(cudaMemcpy(d_table.p, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+  DYNA_TRY(dyna_mh_plan_run_match(p, nullptr));
+  DYNA_TRY(launch_mh_expand(p->counts.p, p->n, p->row_begin, p->row_end, d_table.p, diag, d_out.p, nullptr));
+  DYNA_CUDA(cudaMemcpy(out, d_out.p, sizeof(double) * (size_t)p->n * p->n, cudaMemcpyDeviceToHost));
+  return DYNA_OK;
+}
+
+// several GPUs from one process: one host thread per device, each owning a balanced row block; slabs are gathered
+// to the host and scattered there.  prepare(plan) must leave signatures resident on that plan's device.
+template <class Prepare>
+int mh_matrix_multi(int64_t n, int n_hash, int kind, int gpus, double* out, Prepare prepare) {
+  std::vector<int64_t> bounds((size_t)gpus + 1);
+  DYNA_TRY(dyna_partition_rows(n, nullptr, 0, gpus, bounds.data()));
+  std::vector<double> table;
+  double diag;
+  mh_value_table(n_hash, kind, table, &diag);
+  std::vector<int> rcs((size_t)gpus, DYNA_OK);
+  std::vector<std::string> errs((size_t)gpus);
+  std::vector<std::thread> th;
+  for (int g = 0; g < gpus; ++g)
+    th.emplace_back([&, g]() {
+      int rc = DYNA_OK;
+      dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, bounds[(size_t)g], bounds[(size_t)g + 1], g);
+      if (!p) rc = DYNA_ERR_CUDA;
+      std::vector<uint16_t> slab;
+      if (rc == DYNA_OK) rc = prepare(p);
+      if (rc == DYNA_OK) rc = dyna_mh_plan_run_match(p, nullptr);
+      if (rc == DYNA_OK) {
+        slab.resize((size_t)std::max<int64_t>(p->pairs, 1));
+        rc = dyna_mh_plan_fetch_counts(p, slab.data(), nullptr);
+      }
+      if (rc == DYNA_OK) mh_expand_host(slab.data(), n, p->row_begin, p->row_end, table, diag, out);
+      if (rc != DYNA_OK) errs[(size_t)g] = err_slot();
+      rcs[(size_t)g] = rc;
+      dyna_mh_plan_destroy(p);
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < gpus; ++g)
+    if (rcs[(size_t)g] != DYNA_OK) {
+      err_slot() = errs[(size_t)g];
+      return rcs[(size_t)g];
+    }
+  return DYNA_OK;
+}
+
+}  // namespace
+
+extern "C" int dyna_mh_match_matrix(const uint32_t* sig, int64_t n, int n_hash, int kind, double* out, int n_gpus) {
+  if (n <= 0) return fail(DYNA_ERR_INVALID, "Input sequences vector cannot be empty");
+  if (n_hash <= 0) return fail(DYNA_ERR_INVALID, "Number of hash functions must be positive");
+  if (n_hash > 65535) return fail(DYNA_ERR_UNSUPPORTED, "n_hash > 65535 is not supported (match counts are 16-bit)");
+  if (kind != DYNA_MH_SIMILARITY && kind != DYNA_MH_DISTANCE) return fail(DYNA_ERR_INVALID, "unknown matrix kind %d", kind);
+  int gpus = 1;
+  DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
+  if (n < 2 * 128 * gpus) gpus = 1;
+  if (gpus == 1) {
+    dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
+    if (!p) return DYNA_ERR_CUDA;
+    int rc = dyna_mh_plan_upload_signatures(p, sig, nullptr);
+    if (rc == DYNA_OK) rc = mh_matrix_single(p, kind, out);
+    dyna_mh_plan_destroy(p);
+    return rc;
+  }
+  return mh_matrix_multi(n, n_hash, kind, gpus, out,
+                         [&](dyna_mh_plan* p) { return dyna_mh_plan_upload_signatures(p, sig, nullptr); });
+}
+
+extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets, int64_t n, int k, int n_hash,
+                                 const uint32_t* seeds, double* out, int n_gpus) {
+  DYNA_TRY(check_mh_args(n, k, n_hash));
+  std::vector<uint32_t> own;
+  if (!seeds) {  // reference behaviour: HashFamily(n_hash) seeded from std::random_device (src/minHash.cpp:73,137)
+    own.resize((size_t)n_hash);
+    hashfamily_seeds(dyna_random_seed(), n_hash, own.data());
+    seeds = own.data();
+  }
+  int gpus = 1;
+  DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
+  if (n < 2 * 128 * gpus) gpus = 1;
+  auto prepare = [&](dyna_mh_plan* p) {
+    int rc = dyna_mh_plan_upload_sequences(p, residues, offsets, k, seeds, nullptr);
+    if (rc == DYNA_OK) rc = dyna_mh_plan_run_signatures(p, nullptr);  // every GPU rebuilds all signatures (< 1 ms)
+    return rc;
+  };
+  if (gpus == 1) {
+    dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
+    if (!p) return DYNA_ERR_CUDA;
+    int rc = prepare(p);
+    if (rc == DYNA_OK) rc = mh_matrix_single(p, DYNA_MH_SIMILARITY, out);
+    dyna_mh_plan_destroy(p);
+    return rc;
+  }
+  return mh_matrix_multi(n, n_hash, DYNA_MH_SIMILARITY, gpus, out, prepare);
+}
+
+// =====================================================================================================
+// NW host entry points
+// =====================================================================================================
+extern "C" int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                                  int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint32_t* matches_out,
+                                  uint32_t* length_out) {
+  dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, g_device);
+  if (!p) return err_slot().find("CUDA") != std::string::npos ? DYNA_ERR_CUDA
+                 : (err_slot().find("not supported") != std::string::npos || err_slot().find("exceed") != std::string::npos)
+                     ? DYNA_ERR_UNSUPPORTED
+                     : DYNA_ERR_INVALID;
+  int rc = dyna_nw_plan_run(p, nullptr);
+  if (rc == DYNA_OK) rc = dyna_nw_plan_fetch(p, matches_out, length_out, nullptr);
+  dyna_nw_plan_destroy(p);
+  return rc;
+}
+
+namespace {
+void nw_expand_host(const uint32_t* matches, const uint32_t* length, int64_t n, int64_t row_begin, int64_t row_end, double* out) {
+  const int64_t base = tri_diag_rows(n, row_begin);
+  for (int64_t i = row_begin; i < row_end; ++i) {
+    const int64_t rb = tri_diag_rows(n, i) - base - i;
+    for (int64_t j = i; j < n; ++j) {
+      const double v = static_cast<double>(matches[rb + j]) / static_cast<double>(length[rb + j]);  // 0/0 -> NaN
+      out[i + j * n] = v;
+      out[j + i * n] = v;
+    }
+  }
+}
+int plan_error_code() {
+  const std::string& e = err_slot();
+  if (e.find("CUDA") != std::string::npos) return DYNA_ERR_CUDA;
+  if (e.find("not supported") != std::string::npos || e.find("exceed") != std::string::npos) return DYNA_ERR_UNSUPPORTED;
+  return DYNA_ERR_INVALID;
+}
+}  // namespace
+
+extern "C" int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                                 int gap_open, int gap_ext, double* out, int n_gpus) {
+  if (n == 0) {  // the reference returns a 0 x 0 matrix, but still rejects an unknown matrix name first
+    if (!matrix_name || find_table(matrix_name) < 0)
+      return fail(DYNA_ERR_INVALID, "Invalid substitution matrix name: %s", matrix_name ? matrix_name : "(null)");
+    return DYNA_OK;
+  }
+  int gpus = 1;
+  if (!matrix_name || find_table(matrix_name) < 0)
+    return fail(DYNA_ERR_INVALID, "Invalid substitution matrix name: %s", matrix_name ? matrix_name : "(null)");
+  DYNA_TRY(validate_residues(residues, offsets, n));
+  DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
+  if (n < 64 * gpus) gpus = 1;
+  if (gpus == 1) {
+    dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, 0, n, g_device);
+    if (!p) return plan_error_code();
+    int rc = dyna_nw_plan_run(p, nullptr);
+    if (rc == DYNA_OK) {
+      DevBuf<double> d_out;
+      rc = d_out.alloc((size_t)n * n);
+      if (rc == DYNA_OK) rc = launch_nw_expand(p->matches.p, p->length.p, n, 0, n, d_out.p, nullptr);
+      if (rc == DYNA_OK && cudaMemcpy(out, d_out.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    dyna_nw_plan_destroy(p);
+    return rc;
+  }
+  // several GPUs: row blocks balanced by DP cells (len_i * len_j), one host thread per device, host-side scatter
+  std::vector<int64_t> lens((size_t)n), bounds((size_t)gpus + 1);
+  for (int64_t i = 0; i < n; ++i) lens[(size_t)i] = offsets[i + 1] - offsets[i];
+  DYNA_TRY(dyna_partition_rows(n, lens.data(), 1, gpus, bounds.data()));
+  std::vector<int> rcs((size_t)gpus, DYNA_OK);
+  std::vector<std::string> errs((size_t)gpus);
+  std::vector<std::thread> th;
+  for (int g = 0; g < gpus; ++g)
+    th.emplace_back([&, g]() {
+      int rc = DYNA_OK;
+      dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, bounds[(size_t)g],
+                                            bounds[(size_t)g + 1], g);
+      if (!p) rc = plan_error_code();
+      std::vector<uint32_t> mt, ln;
+      if (rc == DYNA_OK) rc = dyna_nw_plan_run(p, nullptr);
+      if (rc == DYNA_OK) {
+        mt.resize((size_t)std::max<int64_t>(p->pairs, 1));
+        ln.resize((size_t)std::max<int64_t>(p->pairs, 1));
+        rc = dyna_nw_plan_fetch(p, mt.data(), ln.data(), nullptr);
+      }
+      if (rc == DYNA_OK) nw_expand_host(mt.data(), ln.data(), n, p->row_begin, p->row_end, out);
+      if (rc != DYNA_OK) errs[(size_t)g] = err_slot();
+      rcs[(size_t)g] = rc;
+      dyna_nw_plan_destroy(p);
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < gpus; ++g)
+    if (rcs[(size_t)g] != DYNA_OK) {
+      err_slot() = errs[(size_t)g];
+      return rcs[(size_t)g];
+    }
+  return DYNA_OK;
+}

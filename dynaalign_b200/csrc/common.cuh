@@ -1,0 +1,74 @@
+// Shared host/device helpers for the dynaalign_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/dynaalign_b200.h"
+
+namespace dyna {
+
+// ---- thread-local error text, returned by dyna_last_error()
+inline std::string& err_slot() {
+  static thread_local std::string e;
+  return e;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err_slot() = buf;
+  return code;
+}
+
+#define DYNA_CUDA(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return ::dyna::fail(DYNA_ERR_CUDA, "DynaAlign CUDA: %s failed: %s (%s:%d)", #call,             \
+                          cudaGetErrorString(e__), __FILE__, __LINE__);                              \
+  } while (0)
+
+#define DYNA_TRY(expr)            \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != DYNA_OK) return rc__; \
+  } while (0)
+
+// RAII device buffer (cudaMalloc/cudaFree on the current device)
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) count = 1;
+    DYNA_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    return DYNA_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+inline int64_t tri_strict_index(int64_t n, int64_t i, int64_t j) { return i * n - i * (i + 1) / 2 + (j - i - 1); }
+inline int64_t tri_strict_rows(int64_t n, int64_t r) { return r * n - r * (r + 1) / 2; }  // pairs in rows [0,r)
+inline int64_t tri_diag_rows(int64_t n, int64_t r) { return r * n - r * (r - 1) / 2; }    // pairs incl. diagonal in rows [0,r)
+
+constexpr int kNumSMsB200 = 148;
+
+}  // namespace dyna

@@ -1,0 +1,592 @@
+// MinHash kernels for sm_100a.
+//
+//   K1 mh_signature_murmur3_kernel   sig[i][h] = min_p murmur3_32(seq_i[p..p+k), k, seeds[h])
+//                                    (reference: src/minHash.cpp:21-64 hash, :92-105 windows, :140-157 min)
+//   K2 mh_signature_linear_kernel    sig[i][h] = min_x (a_h*x + b_h) mod m over the document's vocabulary ranks
+//                                    (reference: R/minHash.R:104-106, :126-143)
+//   mh_transpose_kernel              row-major -> hash-major layout for the match kernel
+//   K3 mh_match_kernel               counts[i][j] = #{h : sig[i][h]==sig[j][h]}, strict upper triangle
+//                                    (reference: src/minHash.cpp:160-173, R/minHash.R:171-176)
+//   mh_expand_kernel                 counts -> column-major doubles, both triangles + diagonal
+//                                    (reference: src/minHash.cpp:161,174-176; R/minHash.R:175-176)
+//
+// None of this is a dense contraction (the "multiply" is ==), so no tensor cores: the match kernel is an
+// integer-issue-bound register-tiled all-pairs compare fed from shared-memory tiles.
+#include "mh_kernels.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace dyna {
+
+// ------------------------------------------------------------------------------------------------
+// K1: MurmurHash3 signatures
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kSigThreads = 128;
+constexpr int kSigHPT = 4;       // hash functions per thread per pass (independent chains -> ILP)
+constexpr int kSigChunk = 1024;  // window positions staged per shared-memory chunk
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+// the seed-independent part of a murmur3 block / tail: k *= c1; k = rotl(k,15); k *= c2
+__device__ __forceinline__ uint32_t murmur_premix(uint32_t k) {
+  k *= 0xcc9e2d51u;
+  k = rotl32(k, 15);
+  k *= 0x1b873593u;
+  return k;
+}
+__device__ __forceinline__ uint32_t murmur_fmix(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+
+// One CTA per sequence (grid-stride).  Shared memory holds, for a chunk of byte offsets q, the premixed
+// 32-bit block starting at q (bm) and the premixed tail starting at q (tm); a k-mer at p then costs
+// nblocks * (xor, rotl, mad) + xor + fmix per hash function, with every thread of a warp reading the same
+// shared word (broadcast).  Each thread carries kSigHPT independent hash chains.
+__global__ void __launch_bounds__(kSigThreads)
+mh_signature_murmur3_kernel(const uint8_t* __restrict__ res, const int64_t* __restrict__ off, int64_t n, int k,
+                            const uint32_t* __restrict__ seeds, int n_hash, uint32_t* __restrict__ sig) {
+  extern __shared__ uint32_t smem[];
+  const int nblocks = k >> 2, rem = k & 3;
+  const int span = kSigChunk + k;  // entries per table
+  uint32_t* bm = smem;
+  uint32_t* tm = smem + span;
+
+  for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
+    const uint8_t* seq = res + off[s];
+    const int64_t L = off[s + 1] - off[s];
+    const int64_t nwin = L - k + 1;  // <= 0: no window, row stays UINT32_MAX
+    uint32_t* row = sig + s * (int64_t)n_hash;
+
+    for (int h0 = 0; h0 < n_hash; h0 += kSigThreads * kSigHPT) {
+      uint32_t seed[kSigHPT], best[kSigHPT];
+#pragma unroll
+      for (int u = 0; u < kSigHPT; ++u) {
+        int h = h0 + u * kSigThreads + threadIdx.x;
+        seed[u] = h < n_hash ? seeds[h] : 0u;
+        best[u] = 0xFFFFFFFFu;
+      }
+      for (int64_t c0 = 0; c0 < nwin; c0 += kSigChunk) {
+        const int cw = (int)min((int64_t)kSigChunk, nwin - c0);  // windows in this chunk
+        __syncthreads();                                         // previous chunk fully consumed
+        // stage premixed blocks / tails for byte offsets [c0, c0 + cw + k)
+        for (int q = threadIdx.x; q < cw + k; q += kSigThreads) {
+          const int64_t g = c0 + q;
+          if (nblocks && g + 4 <= L) {
+            uint32_t w = (uint32_t)seq[g] | ((uint32_t)seq[g + 1] << 8) | ((uint32_t)seq[g + 2] << 16) |
+                         ((uint32_t)seq[g + 3] << 24);
+            bm[q] = murmur_premix(w);
+          }
+          if (rem && g + rem <= L) {
+            uint32_t w = seq[g];
+            if (rem >= 2) w |= (uint32_t)seq[g + 1] << 8;
+            if (rem >= 3) w |= (uint32_t)seq[g + 2] << 16;
+            tm[q] = murmur_premix(w);
+          }
+        }
+        __syncthreads();
+        for (int p = 0; p < cw; ++p) {
+          uint32_t hv[kSigHPT];
+#pragma unroll
+          for (int u = 0; u < kSigHPT; ++u) hv[u] = seed[u];
+          for (int b = 0; b < nblocks; ++b) {
+            const uint32_t kk = bm[p + 4 * b];
+#pragma unroll
+            for (int u = 0; u < kSigHPT; ++u) {
+              hv[u] ^= kk;
+              hv[u] = rotl32(hv[u], 13) * 5u + 0xe6546b64u;
+            }
+          }
+          if (rem) {
+            const uint32_t kk = tm[p + 4 * nblocks];
+#pragma unroll
+            for (int u = 0; u < kSigHPT; ++u) hv[u] ^= kk;
+          }
+#pragma unroll
+          for (int u = 0; u < kSigHPT; ++u) best[u] = min(best[u], murmur_fmix(hv[u] ^ (uint32_t)k));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSigHPT; ++u) {
+        int h = h0 + u * kSigThreads + threadIdx.x;
+        if (h < n_hash) row[h] = best[u];
+      }
+    }
+  }
+}
+
+// Few hash functions, long sequences: one warp per (sequence, hash); lanes split the windows and the
+// per-sequence minimum is taken with a single warp reduction (redux.sync.min.u32).
+__global__ void __launch_bounds__(kSigThreads)
+mh_signature_murmur3_warpmin_kernel(const uint8_t* __restrict__ res, const int64_t* __restrict__ off, int64_t n, int k,
+                                    const uint32_t* __restrict__ seeds, int n_hash, uint32_t* __restrict__ sig) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kSigThreads / 32;
+  const int nblocks = k >> 2, rem = k & 3;
+  for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
+    const uint8_t* seq = res + off[s];
+    const int64_t L = off[s + 1] - off[s];
+    const int64_t nwin = L - k + 1;
+    for (int h = warp; h < n_hash; h += nwarps) {
+      const uint32_t seed = seeds[h];
+      uint32_t best = 0xFFFFFFFFu;
+      for (int64_t p = lane; p < nwin; p += 32) {
+        const uint8_t* w = seq + p;
+        uint32_t hv = seed;
+        for (int b = 0; b < nblocks; ++b) {
+          uint32_t kk = (uint32_t)w[4 * b] | ((uint32_t)w[4 * b + 1] << 8) | ((uint32_t)w[4 * b + 2] << 16) |
+                        ((uint32_t)w[4 * b + 3] << 24);
+          hv ^= murmur_premix(kk);
+          hv = rotl32(hv, 13) * 5u + 0xe6546b64u;
+        }
+        if (rem) {
+          const uint8_t* t = w + 4 * nblocks;
+          uint32_t kk = t[0];
+          if (rem >= 2) kk |= (uint32_t)t[1] << 8;
+          if (rem >= 3) kk |= (uint32_t)t[2] << 16;
+          hv ^= murmur_premix(kk);
+        }
+        best = min(best, murmur_fmix(hv ^ (uint32_t)k));
+      }
+      best = __reduce_min_sync(0xFFFFFFFFu, best);
+      if (lane == 0) sig[s * (int64_t)n_hash + h] = best;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: linear-mod signatures on vocabulary ranks
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSigThreads)
+mh_signature_linear_kernel(const int32_t* __restrict__ ranks, const int64_t* __restrict__ roff, int64_t n,
+                           const int64_t* __restrict__ a, const int64_t* __restrict__ b, uint64_t m, int n_hash,
+                           uint32_t* __restrict__ sig) {
+  __shared__ uint32_t xs[kSigChunk];
+  for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
+    const int32_t* doc = ranks + roff[s];
+    const int64_t cnt = roff[s + 1] - roff[s];
+    for (int h0 = 0; h0 < n_hash; h0 += kSigThreads) {
+      const int h = h0 + threadIdx.x;
+      const uint64_t ah = h < n_hash ? (uint64_t)a[h] : 0, bh = h < n_hash ? (uint64_t)b[h] : 0;
+      uint64_t best = ~0ull;
+      for (int64_t c0 = 0; c0 < cnt; c0 += kSigChunk) {
+        const int cw = (int)min((int64_t)kSigChunk, cnt - c0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < cw; q += kSigThreads) xs[q] = (uint32_t)doc[c0 + q];
+        __syncthreads();
+        for (int p = 0; p < cw; ++p) {
+          const uint64_t v = (ah * (uint64_t)xs[p] + bh) % m;  // < 2^62 + 2^31: no overflow
+          best = min(best, v);
+        }
+      }
+      if (h < n_hash) sig[s * (int64_t)n_hash + h] = best == ~0ull ? 0xFFFFFFFFu : (uint32_t)best;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout: sig[n][n_hash] -> hash-major sigT[hrows][npitch] and its negation sigTneg (0 - x).
+// Padding hash rows (h >= n_hash) hold 0 in sigT and 1 in sigTneg so that they always MISmatch;
+// padding columns (i >= n) are zero in both and never stored by the match kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void mh_transpose_kernel(const uint32_t* __restrict__ sig, int64_t n, int n_hash, uint32_t* __restrict__ sigT,
+                                    uint32_t* __restrict__ sigTneg, int64_t npitch, int hrows) {
+  __shared__ uint32_t tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;  // sequence block
+  const int h0 = blockIdx.y * 32;               // hash block
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r;
+    const int h = h0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && h < n_hash) ? sig[i * (int64_t)n_hash + h] : 0u;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int h = h0 + r;
+    const int64_t i = i0 + threadIdx.x;
+    if (h < hrows && i < npitch) {
+      const uint32_t v = tile[threadIdx.x][r];
+      sigT[(int64_t)h * npitch + i] = v;
+      sigTneg[(int64_t)h * npitch + i] = (h < n_hash) ? (0u - v) : 1u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: all-pairs match counts (u32 signatures).
+//
+// A CTA owns a 128 x 128 tile of pairs; each of its 256 threads owns 8 x 8 pairs and walks the hash
+// dimension in stages of kMatchBK components staged in shared memory as [h][sequence] (so a thread's
+// 4-wide groups are single 128-bit LDS, A-side reads broadcast across the half-warp).
+//
+// Inner op: the kernel counts MISmatches with DPX, ne += min(a + (-b), 1) -- one VIADDMNMX.U32 per
+// compare plus one 3-input IADD3 per two compares (1.5 issue slots per compare; the naive
+// `cnt += (a == b)` compiles to 3) -- and stores matches = hrows - ne.  The negated operand comes
+// from the sigTneg copy, so no per-element negate is issued.
+//
+// Two loaders feed the same compute core:
+//   * TMA (default): cp.async.bulk.tensor 2-D boxes {128 sequences, kMatchBK hashes} into a 3-stage
+//     mbarrier ring, issued by one elected thread; no registers spent on staging.
+//   * LDG (DYNA_MH_MATCH=ldg): coalesced 32-bit loads with register prefetch, kept as a debugging aid.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMatchThreads = 256;
+constexpr int kMatchStages = 3;
+constexpr int kCsPitch = kMatchBN + 2;  // u16 staging tile pitch (bank skew)
+constexpr uint32_t kStageBytes = 2u * kMatchBK * kMatchBM * sizeof(uint32_t);
+
+struct __align__(128) MatchStage {
+  uint32_t a[kMatchBK][kMatchBM];
+  uint32_t b[kMatchBK][kMatchBN];  // negated
+};
+
+// tile id -> (tile row a, tile col b); tile row a has (T0 - a) tiles, b = 0 is the diagonal tile
+__device__ __forceinline__ void tile_from_id(int64_t t, int64_t T0, int64_t& a, int64_t& b) {
+  const double f = (double)(2 * T0 + 1);
+  int64_t aa = (int64_t)((f - sqrt(f * f - 8.0 * (double)t)) * 0.5);
+  if (aa < 0) aa = 0;
+  while (aa > 0 && aa * T0 - aa * (aa - 1) / 2 > t) --aa;
+  while ((aa + 1) * T0 - (aa + 1) * aa / 2 <= t) ++aa;
+  a = aa;
+  b = t - (aa * T0 - aa * (aa - 1) / 2);
+}
+
+__device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty, int tx, uint32_t (&ne)[8][8]) {
+#pragma unroll
+  for (int hh = 0; hh < kMatchBK; hh += 2) {
+    uint32_t av[2][8], bv[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh + u][ty * 4]);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh + u][64 + ty * 4]);
+      const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh + u][tx * 4]);
+      const uint4 b1 = *reinterpret_cast<const uint4*>(&st.b[hh + u][64 + tx * 4]);
+      av[u][0] = a0.x; av[u][1] = a0.y; av[u][2] = a0.z; av[u][3] = a0.w;
+      av[u][4] = a1.x; av[u][5] = a1.y; av[u][6] = a1.z; av[u][7] = a1.w;
+      bv[u][0] = b0.x; bv[u][1] = b0.y; bv[u][2] = b0.z; bv[u][3] = b0.w;
+      bv[u][4] = b1.x; bv[u][5] = b1.y; bv[u][6] = b1.z; bv[u][7] = b1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        ne[i][j] += __viaddmin_u32(av[0][i], bv[0][j], 1u) + __viaddmin_u32(av[1][i], bv[1][j], 1u);
+  }
+}
+
+// counts tile -> packed strict upper triangle, staged through shared memory for coalesced rows
+__device__ __forceinline__ void match_store_tile(uint16_t (*cs)[kCsPitch], const uint32_t (&ne)[8][8], int hrows, int ty,
+                                                 int tx, int lx, int lw, int64_t r0, int64_t c0, int64_t n,
+                                                 int64_t row_end, int64_t slab_base, uint16_t* __restrict__ counts) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ri = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cj = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+      cs[ri][cj] = (uint16_t)((uint32_t)hrows - ne[i][j]);
+    }
+  }
+  __syncthreads();
+  // warp lw writes rows lw, lw+8, ...; one row = 128 consecutive u16 of the packed triangle
+  for (int r = lw; r < kMatchBM; r += kMatchThreads / 32) {
+    const int64_t i = r0 + r;
+    if (i >= row_end) break;
+    const int64_t rowbase = i * n - i * (i + 1) / 2 - i - 1 - slab_base;  // + j
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int cj = lx + 32 * v;
+      const int64_t j = c0 + cj;
+      if (j > i && j < n) counts[rowbase + j] = cs[r][cj];
+    }
+  }
+}
+
+// ---- mbarrier / TMA PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();  // a lost TMA must fault loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct TmapPair {
+  alignas(64) unsigned char a[128];  // CUtensorMap over sigT
+  alignas(64) unsigned char b[128];  // CUtensorMap over sigTneg
+};
+
+__global__ void __launch_bounds__(kMatchThreads, 2)
+mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int64_t n, int64_t row_begin, int64_t row_end,
+                    uint16_t* __restrict__ counts, int64_t slab_base, int64_t T0, int64_t num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MatchStage* stages = reinterpret_cast<MatchStage*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kMatchStages * sizeof(MatchStage));
+  uint16_t(*cs)[kCsPitch] = reinterpret_cast<uint16_t(*)[kCsPitch]>(smem_raw);  // aliases the stage ring after the loop
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lx = tid & 31, lw = tid >> 5;
+  const int nkb = hrows / kMatchBK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kMatchStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t it = 0;  // running stage counter across tiles: slot = it % S, parity = (it / S) & 1
+  for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int64_t ta, tb;
+    tile_from_id(t, T0, ta, tb);
+    const int64_t r0 = row_begin + ta * kMatchBM;
+    const int64_t c0 = r0 + tb * kMatchBN;
+
+    uint32_t ne[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ne[i][j] = 0;
+
+    auto issue = [&](int kb, uint32_t slot) {
+      mbar_expect_tx(&full[slot], kStageBytes);
+      tma_load_2d(&stages[slot].a[0][0], tm.a, (int)r0, kb * kMatchBK, &full[slot]);
+      tma_load_2d(&stages[slot].b[0][0], tm.b, (int)c0, kb * kMatchBK, &full[slot]);
+    };
+    if (tid == 0) {
+      // generic-proxy writes of the previous tile's staging (cs) must be ordered before async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int p = 0; p < kMatchStages - 1 && p < nkb; ++p) issue(p, (it + p) % kMatchStages);
+    }
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const uint32_t slot = it % kMatchStages;
+      if (tid == 0 && kb + kMatchStages - 1 < nkb) issue(kb + kMatchStages - 1, (it + kMatchStages - 1) % kMatchStages);
+      mbar_wait(&full[slot], (it / kMatchStages) & 1u);
+      match_stage_compute(stages[slot], ty, tx, ne);
+      __syncthreads();  // slot free for the load issued at the top of the next iteration
+    }
+    match_store_tile(cs, ne, hrows, ty, tx, lx, lw, r0, c0, n, row_end, slab_base, counts);
+    __syncthreads();  // cs (aliasing the ring) fully read before the next tile's loads land
+  }
+}
+
+__global__ void __launch_bounds__(kMatchThreads, 2)
+mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, const uint32_t* __restrict__ sigTneg, int64_t npitch, int hrows,
+                    int64_t n, int64_t row_begin, int64_t row_end, uint16_t* __restrict__ counts, int64_t slab_base,
+                    int64_t T0, int64_t num_tiles) {
+  __shared__ __align__(128) unsigned char smem_raw[(sizeof(MatchStage) > sizeof(uint16_t) * kMatchBM * kCsPitch)
+                                                       ? sizeof(MatchStage)
+                                                       : sizeof(uint16_t) * kMatchBM * kCsPitch];
+  MatchStage& st = *reinterpret_cast<MatchStage*>(smem_raw);
+  uint16_t(*cs)[kCsPitch] = reinterpret_cast<uint16_t(*)[kCsPitch]>(smem_raw);
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lx = tid & 31, lw = tid >> 5;  // loader: warp lw loads hash rows lw, lw+8 of the stage
+  const int nkb = hrows / kMatchBK;
+
+  for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int64_t ta, tb;
+    tile_from_id(t, T0, ta, tb);
+    const int64_t r0 = row_begin + ta * kMatchBM;
+    const int64_t c0 = r0 + tb * kMatchBN;
+    uint32_t ne[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ne[i][j] = 0;
+
+    uint32_t pa[2][4], pb[2][4];
+    auto prefetch = [&](int kb) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int64_t rowoff = (int64_t)(kb * kMatchBK + lw + 8 * q) * npitch;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          pa[q][v] = __ldg(sigT + rowoff + r0 + lx + 32 * v);
+          pb[q][v] = __ldg(sigTneg + rowoff + c0 + lx + 32 * v);
+        }
+      }
+    };
+    prefetch(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          st.a[lw + 8 * q][lx + 32 * v] = pa[q][v];
+          st.b[lw + 8 * q][lx + 32 * v] = pb[q][v];
+        }
+      __syncthreads();
+      if (kb + 1 < nkb) prefetch(kb + 1);
+      match_stage_compute(st, ty, tx, ne);
+    }
+    __syncthreads();
+    match_store_tile(cs, ne, hrows, ty, tx, lx, lw, r0, c0, n, row_end, slab_base, counts);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// expansion of a counts slab into the R matrix: value table lookup (host computes the n_hash+1 doubles
+// with the reference's exact arithmetic, incl. R's long-double mean())
+// ------------------------------------------------------------------------------------------------
+__global__ void mh_expand_kernel(const uint16_t* __restrict__ counts, int64_t n, int64_t row_begin, int64_t row_end,
+                                 int64_t slab_base, const double* __restrict__ table, double diag,
+                                 double* __restrict__ out) {
+  // one block row per matrix row i; threads over j
+  for (int64_t i = row_begin + blockIdx.y; i < row_end; i += gridDim.y) {
+    const int64_t rowbase = i * n - i * (i + 1) / 2 - i - 1 - slab_base;
+    for (int64_t j = i + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+      if (j == i) {
+        out[i + i * n] = diag;
+      } else {
+        const double v = table[counts[rowbase + j]];
+        out[i + j * n] = v;
+        out[j + i * n] = v;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------
+int launch_mh_signature_murmur3(const uint8_t* d_res, const int64_t* d_off, int64_t n, int64_t max_len, int k,
+                                const uint32_t* d_seeds, int n_hash, uint32_t* d_sig, cudaStream_t st) {
+  if (n == 0) return DYNA_OK;
+  const int grid = (int)std::min<int64_t>(n, (int64_t)kNumSMsB200 * 64);
+  // few hash functions on long sequences: lanes over windows + warp min; otherwise one thread per hash function
+  if (n_hash < 64 && max_len >= 256) {
+    mh_signature_murmur3_warpmin_kernel<<<grid, kSigThreads, 0, st>>>(d_res, d_off, n, k, d_seeds, n_hash, d_sig);
+  } else {
+    const size_t smem = (size_t)(kSigChunk + k) * 2 * sizeof(uint32_t);
+    mh_signature_murmur3_kernel<<<grid, kSigThreads, smem, st>>>(d_res, d_off, n, k, d_seeds, n_hash, d_sig);
+  }
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_signature_linear(const int32_t* d_ranks, const int64_t* d_roff, int64_t n, const int64_t* d_a,
+                               const int64_t* d_b, int64_t m, int n_hash, uint32_t* d_sig, cudaStream_t st) {
+  if (n == 0) return DYNA_OK;
+  const int grid = (int)std::min<int64_t>(n, (int64_t)kNumSMsB200 * 64);
+  mh_signature_linear_kernel<<<grid, kSigThreads, 0, st>>>(d_ranks, d_roff, n, d_a, d_b, (uint64_t)m, n_hash, d_sig);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_transpose(const uint32_t* d_sig, int64_t n, int n_hash, uint32_t* d_sigT, uint32_t* d_sigTneg,
+                        int64_t npitch, int hrows, cudaStream_t st) {
+  dim3 grid((unsigned)((npitch + 31) / 32), (unsigned)((hrows + 31) / 32));
+  dim3 block(32, 8);
+  mh_transpose_kernel<<<grid, block, 0, st>>>(d_sig, n, n_hash, d_sigT, d_sigTneg, npitch, hrows);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+// ---- tensor maps: cuTensorMapEncodeTiled is reached through the runtime's driver entry point query so the
+// library needs no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_sig_tmap(void* out128, const uint32_t* base, int64_t npitch, int hrows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DYNA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+      return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)npitch, (cuuint64_t)hrows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)npitch * sizeof(uint32_t)};
+  const cuuint32_t box[2] = {(cuuint32_t)kMatchBM, (cuuint32_t)kMatchBK};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  memcpy(out128, &tmap, 128);
+  return DYNA_OK;
+}
+
+int launch_mh_match(const uint32_t* d_sigT, const uint32_t* d_sigTneg, int64_t npitch, int hrows, int64_t n,
+                    int64_t row_begin, int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches) {
+  if (launches) *launches = 0;
+  if (row_end <= row_begin || n < 2) return DYNA_OK;
+  const int64_t T0 = (n - row_begin + kMatchBM - 1) / kMatchBM;
+  const int64_t NA = (row_end - row_begin + kMatchBM - 1) / kMatchBM;
+  const int64_t num_tiles = NA * T0 - NA * (NA - 1) / 2;
+  const int64_t slab_base = tri_strict_rows(n, row_begin);
+  const int grid = (int)std::min<int64_t>(num_tiles, (int64_t)kNumSMsB200 * 2);
+  const char* mode = getenv("DYNA_MH_MATCH");
+  if (mode && strcmp(mode, "ldg") == 0) {
+    mh_match_ldg_kernel<<<grid, kMatchThreads, 0, st>>>(d_sigT, d_sigTneg, npitch, hrows, n, row_begin, row_end,
+                                                        d_counts, slab_base, T0, num_tiles);
+  } else {
+    if (npitch >= (1ll << 31)) return fail(DYNA_ERR_UNSUPPORTED, "too many sequences for the TMA match kernel");
+    TmapPair tm;
+    DYNA_TRY(encode_sig_tmap(tm.a, d_sigT, npitch, hrows));
+    DYNA_TRY(encode_sig_tmap(tm.b, d_sigTneg, npitch, hrows));
+    const size_t smem = kMatchStages * sizeof(MatchStage) + kMatchStages * sizeof(uint64_t);
+    static_assert(kMatchStages * sizeof(MatchStage) >= sizeof(uint16_t) * kMatchBM * kCsPitch, "staging tile must fit the ring");
+    static bool attr_done = false;
+    if (!attr_done) {
+      DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    mh_match_tma_kernel<<<grid, kMatchThreads, smem, st>>>(tm, hrows, n, row_begin, row_end, d_counts, slab_base, T0,
+                                                           num_tiles);
+  }
+  DYNA_CUDA(cudaGetLastError());
+  if (launches) *launches = 1;
+  return DYNA_OK;
+}
+
+int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,
+                     double diag, double* d_out, cudaStream_t st) {
+  if (row_end <= row_begin) return DYNA_OK;
+  const int64_t slab_base = tri_strict_rows(n, row_begin);
+  dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)std::min<int64_t>(row_end - row_begin, 32768));
+  mh_expand_kernel<<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, slab_base, d_table, diag, d_out);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+}  // namespace dyna

@@ -1,0 +1,34 @@
+// MinHash device kernels (sm_100a): launch wrappers.  See mh_kernels.cu for the kernels themselves.
+#pragma once
+#include "common.cuh"
+
+namespace dyna {
+
+// Device layout of a signature set used by the match kernel: hash-major ("sigT"), i.e. row h holds the
+// h-th signature component of every sequence, padded so every tile read is in bounds:
+//   sigT[h * npitch + i],  h < hrows (= n_hash rounded up to kMatchBK), i < npitch (>= n + 256, multiple of 128)
+constexpr int kMatchBM = 128;  // pairs tile: rows
+constexpr int kMatchBN = 128;  // pairs tile: cols
+constexpr int kMatchBK = 16;   // hash components per pipeline stage
+
+inline int64_t mh_npitch(int64_t n) { return ((n + 127) / 128) * 128 + 256; }
+inline int mh_hrows(int n_hash) { return ((n_hash + kMatchBK - 1) / kMatchBK) * kMatchBK; }
+
+// K1: signatures from raw residues with MurmurHash3_x86_32 (src/minHash.cpp:21-64,140-157)
+int launch_mh_signature_murmur3(const uint8_t* d_res, const int64_t* d_off, int64_t n, int64_t max_len, int k,
+                                const uint32_t* d_seeds, int n_hash, uint32_t* d_sig, cudaStream_t st);
+// K2: signatures from vocabulary ranks with (a*x+b) mod m (R/minHash.R:104-106,126-143)
+int launch_mh_signature_linear(const int32_t* d_ranks, const int64_t* d_roff, int64_t n, const int64_t* d_a,
+                               const int64_t* d_b, int64_t m, int n_hash, uint32_t* d_sig, cudaStream_t st);
+// row-major sig[n][n_hash] -> hash-major sigT[hrows][npitch] plus its negation sigTneg (see mh_kernels.cu)
+int launch_mh_transpose(const uint32_t* d_sig, int64_t n, int n_hash, uint32_t* d_sigT, uint32_t* d_sigTneg,
+                        int64_t npitch, int hrows, cudaStream_t st);
+// K3: match counts for rows [row_begin,row_end) into the packed strict-upper-triangle slab
+int launch_mh_match(const uint32_t* d_sigT, const uint32_t* d_sigTneg, int64_t npitch, int hrows, int64_t n,
+                    int64_t row_begin, int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches);
+// expand a counts slab into the column-major double matrix (both triangles + diagonal of the slab's rows):
+// out = table[count]; the n_hash+1 table entries are computed on the host with the reference's arithmetic
+int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,
+                     double diag, double* d_out, cudaStream_t st);
+
+}  // namespace dyna

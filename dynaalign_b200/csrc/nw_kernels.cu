@@ -1,0 +1,443 @@
+// Needleman-Wunsch identity kernels for sm_100a.
+//
+// What is computed (reference: calculate_similarity, src/pairwiseSeqAlign.cpp:209-313): a three-state affine-gap
+// global alignment whose result is NOT the score but (matches, alignment_length) of the traceback path, with the
+// reference's exact quirks -- M overwritten by the winning state (:273-278), tie-break D >= U >= L (:271-279),
+// border gaps one extension cheaper than interior gaps (:226,:233 vs :255,:260), raw-character equality for
+// matches (:294), row sequence = lower index (:340-346).
+//
+// How (no traceback matrix): every cell has exactly one predecessor, so the pair (matches, #diagonal steps) is
+// carried forward with the scores; alignment_length = m + n - #diagonal steps.  Per cell, with
+//   F = Ix[i][j]  (carried down the column, already holding max(H_up - (go+ge), F_up - ge)),
+//   E = Iy[i][j]  (carried along the row, same form), diag = max(M,Ix,Iy)[i-1][j-1]:
+//   Mraw = diag + s                       IADD
+//   H    = max3(Mraw, F, E)               VIMNMX3            (DPX)
+//   D    = (Mraw == H); U = (F >= E)      2 x ISETP
+//   stat = D ? stat_diag + inc : (U ? stat_up : stat_left)   IADD + 2 x SEL   (inc = 1 | eq << 16)
+//   E'   = max(H - (go+ge), E - ge)       IADD + VIADDMNMX   (DPX)
+//   F'   = max(H - (go+ge), F - ge)       IADD + VIADDMNMX   (DPX)
+// Storing E'/F' (the value the NEXT cell needs) instead of Iy/Ix makes the reference's asymmetric borders pure
+// initial values: the border's "open source" M[i][0] = M[0][j] = NEG never has to coexist with the border's
+// "diagonal source" max(M,Ix,Iy) = -go-(k-1)ge in one register.
+//
+// The substitution scores come from a query profile of the ROW sequence staged in shared memory:
+// prof[c][row] = (int8 S[a_row][c], uint8 a_row == c) for the 24 residue classes c, so one step of a lane needs a
+// single contiguous read of R 16-bit entries, decoded with two PRMT per cell (sign-extended score, stat increment).
+//
+//   K5 nw_warp_kernel<R>    one warp per pair: lane l owns rows [l*R, l*R+R) in registers and walks the columns;
+//                           lane l is one column behind lane l-1 (anti-diagonal wavefront) and receives the bottom
+//                           row of its upper neighbour (H, F, stat) through __shfl_up_sync.  A CTA shares one row
+//                           sequence (one profile) across its 8 warps.  Rows longer than 32*R take several passes,
+//                           the last lane spilling its bottom row to a per-warp global scratch line.
+//   K4 nw_thread_kernel<R>  one thread per pair for short rows (<= 32 residues): the whole column strip lives in
+//                           the thread's registers, no shuffles; lanes of a warp share the row sequence, so
+//                           profile reads are bank-conflict free (distinct residue class -> distinct bank).
+#include "nw_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+
+namespace dyna {
+namespace {
+
+constexpr int kNeg = INT_MIN / 2;  // the reference's "minus infinity" (src/pairwiseSeqAlign.cpp:216)
+
+__device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+__device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+__device__ __forceinline__ int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+
+// border diagonal source: max(M,Ix,Iy) at (k,0) or (0,k):  Bd(0) = 0, Bd(k) = -go - (k-1)*ge
+__device__ __forceinline__ int border_diag(int k, int go, int ge) { return k == 0 ? 0 : wsub(-go, wmul(k - 1, ge)); }
+
+template <int R>
+struct Strip {
+  static constexpr int RP = R + (R & 1);      // 16-bit entries per lane strip, padded to even
+  static constexpr int RW = RP / 2;           // 32-bit words actually read per step
+  static constexpr int RWS = (RP / 2) | 1;    // word stride between strips: odd -> conflict-free across lanes
+};
+
+// PTX prmt with full selector semantics (bit 3 of a selector nibble replicates the sign of the selected byte;
+// the __byte_perm intrinsic masks that bit away).
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+  return d;
+}
+
+// Gap-extension slanting.  With SLANT every DP value of cell (i,j) is stored as value + (i+j)*ge.  All
+// comparisons inside a cell share the offset, the extension term cancels from both gap recurrences
+//   E'(i,j+1) = max(H - go, E)      F'(i+1,j) = max(H - go, F)        (one VIADDMNMX each, no IADD)
+// and the diagonal step picks up + 2*ge, which is folded into the profile's score byte.  Exact as long as
+// nothing overflows (checked on the host); without SLANT the textbook form with explicit "- ge" is used.
+template <bool SLANT>
+struct Gap {
+  int neg_open;  // added to H when a gap opens:  SLANT ? -go : -(go+ge)
+  int ext;       // subtracted when a gap extends: SLANT ? 0 : ge
+  int sl;        // slant per unit of (i+j):       SLANT ? ge : 0
+};
+
+// One column of a strip of R rows: reads the column to the left (Ho, So), writes this column (Hn, Sn); E is
+// updated in place.  Ping-ponging H and S between two register sets keeps the loop free of register moves.
+template <int R, bool SLANT>
+__device__ __forceinline__ void strip_column(const int (&Ho)[R], const uint32_t (&So)[R], int (&Hn)[R], uint32_t (&Sn)[R],
+                                             int (&El)[R], const uint32_t (&pw)[Strip<R>::RW], int diagH, uint32_t diagS,
+                                             int F, uint32_t upS, const Gap<SLANT>& g, uint32_t one, int& outF) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t w = pw[k >> 1];
+    // entry layout (16 bit): low byte = int8 score (+ 2*ge when slanted), high byte = 1 if residues are equal
+    const int s = (k & 1) ? (int)prmt<0xAAA2>(w, 0u) : (int)prmt<0x8880>(w, 0u);
+    const uint32_t inc = (k & 1) ? prmt<0x5354>(w, one) : prmt<0x5154>(w, one);  // 1 | eq << 16
+    const int E = El[k];
+    const int Mraw = diagH + s;
+    const int H = __vimax3_s32(Mraw, F, E);
+    const bool pD = (Mraw == H);  // Mraw >= F && Mraw >= E
+    const bool pU = (F >= E);
+    uint32_t S = pU ? upS : So[k];
+    if (pD) S = diagS + inc;
+    diagH = Ho[k];
+    diagS = So[k];
+    Hn[k] = H;
+    Sn[k] = S;
+    if (SLANT) {
+      El[k] = __viaddmax_s32(H, g.neg_open, E);
+      F = __viaddmax_s32(H, g.neg_open, F);
+    } else {
+      El[k] = __viaddmax_s32(H, g.neg_open, E - g.ext);
+      F = __viaddmax_s32(H, g.neg_open, F - g.ext);
+    }
+    upS = S;
+  }
+  outF = F;
+}
+
+// profile of rows [row0, row0 + LANES*R) of the row sequence (length m) into shared memory, strip-major per class
+template <int R, int LANES>
+__device__ __forceinline__ void build_profile(uint32_t* prof, const uint8_t* __restrict__ a, int m, int row0,
+                                              const int8_t* __restrict__ sub, int bias, int tid, int nthreads) {
+  using S = Strip<R>;
+  uint16_t* p16 = reinterpret_cast<uint16_t*>(prof);
+  constexpr int per_class = LANES * S::RWS * 2;  // 16-bit entries per residue class (incl. padding)
+  for (int idx = tid; idx < 24 * LANES * S::RP; idx += nthreads) {
+    const int c = idx / (LANES * S::RP);
+    const int rem = idx - c * (LANES * S::RP);
+    const int lane = rem / S::RP, k = rem - lane * S::RP;
+    const int r = row0 + lane * R + k;
+    uint16_t e = 0;
+    if (k < R && r < m) {
+      const int ar = a[r];
+      e = (uint16_t)((uint8_t)(sub[ar * 24 + c] + bias)) | (uint16_t)((ar == c) ? 0x0100 : 0);
+    }
+    p16[c * per_class + lane * (S::RWS * 2) + k] = e;
+  }
+}
+
+__device__ __forceinline__ int64_t pair_slot(int64_t n, int64_t i, int64_t j, int64_t slab_base) {
+  return i * n - i * (i - 1) / 2 + (j - i) - slab_base;
+}
+
+template <bool SLANT>
+__device__ __forceinline__ Gap<SLANT> make_gap(int go, int ge) {
+  Gap<SLANT> g;
+  g.neg_open = SLANT ? wsub(0, go) : wsub(0, wadd(go, ge));
+  g.ext = SLANT ? 0 : ge;
+  g.sl = SLANT ? ge : 0;
+  return g;
+}
+// Ix[1][j] = Iy[i][1] = max(NEG-(go+ge), NEG-ge)  (src/pairwiseSeqAlign.cpp:255-262 applied to the border)
+__device__ __forceinline__ int neg_init_value(int go, int ge) { return max(wsub(kNeg, wadd(go, ge)), wsub(kNeg, ge)); }
+
+// ------------------------------------------------------------------------------------------------
+// K5: one warp per pair
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpThreads = 256;
+
+template <int R, bool SLANT, bool MULTIPASS>
+__global__ void __launch_bounds__(kWarpThreads)
+nw_warp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units, int32_t* __restrict__ scratch,
+               int max_cols) {
+  using S = Strip<R>;
+  __shared__ uint32_t prof[24 * 32 * S::RWS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = kWarpThreads / 32;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const Gap<SLANT> g = make_gap<SLANT>(go, ge);
+  const int neg_init = neg_init_value(go, ge);
+  const uint32_t one = d.one;  // opaque 1 (kept in a register so PRMT can take an immediate selector)
+  const unsigned full = 0xFFFFFFFFu;
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row;
+    const int m = d.off[row + 1] - d.off[row];
+    const uint8_t* a = d.codes + d.off[row];
+    const int npass = MULTIPASS ? (m + 32 * R - 1) / (32 * R) : 1;
+    // multipass units carry at most one pair per warp, so one scratch line per warp persists across passes
+    int32_t* wscr = MULTIPASS ? scratch + ((int64_t)blockIdx.x * nwarps + warp) * 3 * (int64_t)max_cols : nullptr;
+
+    for (int pass = 0; pass < npass; ++pass) {
+      const int row0 = pass * 32 * R;
+      __syncthreads();  // previous profile no longer in use
+      build_profile<R, 32>(prof, a, m, row0, d.sub, 2 * g.sl, tid, kWarpThreads);
+      __syncthreads();
+      const bool last_pass = (pass == npass - 1);
+      const int lm = last_pass ? (m - 1 - row0) / R : 31;  // last lane with real rows in this pass
+      const int km = (m - 1 - row0) - lm * R;              // row of (m, .) inside lane lm (last pass only)
+      const int r0 = row0 + lane * R;                      // 0-based first row of this lane's strip
+
+      for (int jj = warp; jj < un.j_count; jj += nwarps) {
+        const int j = un.j_begin + jj;
+        const int n = d.off[j + 1] - d.off[j];
+        const uint8_t* __restrict__ b = d.codes + d.off[j];
+
+        // two register sets for (H, S): step t reads set (t&1), writes set ((t+1)&1); both start as the border
+        int H0[R], H1[R], El[R];
+        uint32_t S0[R], S1[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int i = r0 + k + 1;                                     // 1-based DP row
+          H0[k] = H1[k] = wadd(wsub(-go, wmul(i - 1, ge)), wmul(i, g.sl));  // Bd(i) at column 0
+          El[k] = wadd(neg_init, wmul(i + 1, g.sl));                    // Iy[i][1]
+          S0[k] = S1[k] = 0u;
+        }
+        int prevUpH = wadd(border_diag(r0, go, ge), wmul(r0, g.sl));  // diagonal source (r0, 0)
+        uint32_t prevUpS = 0u;
+        int outH = 0, outF = 0;
+        uint32_t outS = 0u;
+        const int T = n + lm;
+        for (int t0 = 0; t0 < T; t0 += 2) {
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int t = t0 + ph;
+            const int jc = t - lane;  // 0-based column handled by this lane in this step
+            int rH = __shfl_up_sync(full, outH, 1);
+            int rF = __shfl_up_sync(full, outF, 1);
+            uint32_t rS = __shfl_up_sync(full, outS, 1);
+            if (lane == 0) {
+              if (!MULTIPASS || pass == 0) {
+                rH = wadd(wsub(-go, wmul(t, ge)), wmul(t + 1, g.sl));  // Bd(t+1) at (0, t+1)
+                rF = wadd(neg_init, wmul(t + 2, g.sl));                // Ix[1][t+1]
+                rS = 0u;
+              } else if (t < n) {
+                rH = wscr[3 * t + 0];
+                rF = wscr[3 * t + 1];
+                rS = (uint32_t)wscr[3 * t + 2];
+              }
+            }
+            if (jc >= 0 && jc < n && lane <= lm) {
+              const int c = b[jc];
+              uint32_t pw[S::RW];
+              const uint32_t* pp = prof + c * (32 * S::RWS) + lane * S::RWS;
+#pragma unroll
+              for (int w = 0; w < S::RW; ++w) pw[w] = pp[w];
+              // parity of the step as seen by this lane: its first column always reads set (lane&1)... use t
+              if (((t0 + ph) & 1) == 0) {
+                strip_column<R, SLANT>(H0, S0, H1, S1, El, pw, prevUpH, prevUpS, rF, rS, g, one, outF);
+                outH = H1[R - 1];
+                outS = S1[R - 1];
+              } else {
+                strip_column<R, SLANT>(H1, S1, H0, S0, El, pw, prevUpH, prevUpS, rF, rS, g, one, outF);
+                outH = H0[R - 1];
+                outS = S0[R - 1];
+              }
+              prevUpH = rH;
+              prevUpS = rS;
+              if (MULTIPASS && !last_pass && lane == 31) {  // bottom row of this pass feeds lane 0 of the next
+                wscr[3 * jc + 0] = outH;
+                wscr[3 * jc + 1] = outF;
+                wscr[3 * jc + 2] = (int32_t)outS;
+              }
+            }
+          }
+        }
+        if (last_pass) {
+          // lane lm finished its last column at step t = lm + n - 1, which wrote set ((lm + n) & 1)
+          const bool in1 = (((lm + n) & 1) != 0);
+          uint32_t res = 0u;
+#pragma unroll
+          for (int k = 0; k < R; ++k)
+            if (k == km) res = in1 ? S1[k] : S0[k];
+          res = __shfl_sync(full, res, lm);
+          if (lane == 0) {
+            const int64_t slot = pair_slot(d.n, row, j, d.slab_base);
+            d.matches[slot] = res >> 16;
+            d.length[slot] = (uint32_t)(m + n) - (res & 0xFFFFu);
+          }
+        }
+        if (MULTIPASS) __syncwarp();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: one thread per pair (rows <= R <= 32)
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreadThreads = 128;
+
+template <int R, bool SLANT>
+__global__ void __launch_bounds__(kThreadThreads)
+nw_thread_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  using S = Strip<R>;
+  __shared__ uint32_t prof[24 * S::RWS];
+  const int tid = threadIdx.x;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const Gap<SLANT> g = make_gap<SLANT>(go, ge);
+  const int neg_init = neg_init_value(go, ge);
+  const uint32_t one = d.one;
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row;
+    const int m = d.off[row + 1] - d.off[row];
+    __syncthreads();
+    build_profile<R, 1>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * g.sl, tid, kThreadThreads);
+    __syncthreads();
+    for (int jj = tid; jj < un.j_count; jj += kThreadThreads) {
+      const int j = un.j_begin + jj;
+      const int n = d.off[j + 1] - d.off[j];
+      const uint8_t* __restrict__ b = d.codes + d.off[j];
+      int H0[R], H1[R], El[R];
+      uint32_t S0[R], S1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int i = k + 1;
+        H0[k] = H1[k] = wadd(wsub(-go, wmul(i - 1, ge)), wmul(i, g.sl));
+        El[k] = wadd(neg_init, wmul(i + 1, g.sl));
+        S0[k] = S1[k] = 0u;
+      }
+      int diagH = 0;  // Bd(0) at (0,0), slant 0
+      int outF;
+      for (int t0 = 0; t0 < n; t0 += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const int t = t0 + ph;
+          if (t < n) {
+            const int c = b[t];
+            uint32_t pw[S::RW];
+#pragma unroll
+            for (int w = 0; w < S::RW; ++w) pw[w] = prof[c * S::RWS + w];
+            const int rF = wadd(neg_init, wmul(t + 2, g.sl));  // Ix[1][t+1]
+            if (ph == 0)
+              strip_column<R, SLANT>(H0, S0, H1, S1, El, pw, diagH, 0u, rF, 0u, g, one, outF);
+            else
+              strip_column<R, SLANT>(H1, S1, H0, S0, El, pw, diagH, 0u, rF, 0u, g, one, outF);
+            diagH = wadd(wsub(-go, wmul(t, ge)), wmul(t + 1, g.sl));  // Bd(t+1) at (0, t+1) for the next column
+          }
+        }
+      }
+      const bool in1 = ((n & 1) != 0);
+      uint32_t res = 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (k == m - 1) res = in1 ? S1[k] : S0[k];
+      const int64_t slot = pair_slot(d.n, row, j, d.slab_base);
+      d.matches[slot] = res >> 16;
+      d.length[slot] = (uint32_t)(m + n) - (res & 0xFFFFu);
+    }
+  }
+}
+
+// rows of length 0: no DP; the path is n left moves -> matches 0, length n (0/0 -> NaN handled at the division)
+__global__ void nw_empty_rows_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    for (int jj = threadIdx.x; jj < un.j_count; jj += blockDim.x) {
+      const int j = un.j_begin + jj;
+      const int64_t slot = pair_slot(d.n, un.row, j, d.slab_base);
+      d.matches[slot] = 0u;
+      d.length[slot] = (uint32_t)(d.off[j + 1] - d.off[j]);
+    }
+  }
+}
+
+__global__ void nw_expand_kernel(const uint32_t* __restrict__ matches, const uint32_t* __restrict__ length, int64_t n,
+                                 int64_t row_begin, int64_t row_end, int64_t slab_base, double* __restrict__ out) {
+  for (int64_t i = row_begin + blockIdx.y; i < row_end; i += gridDim.y) {
+    const int64_t rowbase = i * n - i * (i - 1) / 2 - i - slab_base;  // + j
+    for (int64_t j = i + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+      // static_cast<double>(matches) / alignment_length (src/pairwiseSeqAlign.cpp:311); IEEE double divide, 0/0 = NaN
+      const double v = __ddiv_rn((double)matches[rowbase + j], (double)length[rowbase + j]);
+      out[i + j * n] = v;
+      out[j + i * n] = v;
+    }
+  }
+}
+
+template <int R>
+int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (slant) nw_warp_kernel<R, true, false><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units, nullptr, 0);
+  else       nw_warp_kernel<R, false, false><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units, nullptr, 0);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_warp_multipass(bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, int32_t* d_scratch,
+                          int max_cols, cudaStream_t st) {
+  const int grid = std::min(num_units, kNwMultiPassGrid);
+  if (slant)
+    nw_warp_kernel<kNwWarpMaxR, true, true><<<grid, kWarpThreads, 0, st>>>(d, d_units, num_units, d_scratch, max_cols);
+  else
+    nw_warp_kernel<kNwWarpMaxR, false, true><<<grid, kWarpThreads, 0, st>>>(d, d_units, num_units, d_scratch, max_cols);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+}  // namespace
+
+int launch_nw_empty_rows(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  nw_empty_rows_kernel<<<std::min(num_units, kNumSMsB200 * 8), 256, 0, st>>>(d, d_units, num_units);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_thread(int R, bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR)                                                                                        \
+  case RR:                                                                                                   \
+    if (slant) nw_thread_kernel<RR, true><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units);      \
+    else       nw_thread_kernel<RR, false><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units);     \
+    break;
+    DYNA_CASE(4) DYNA_CASE(8) DYNA_CASE(12) DYNA_CASE(16) DYNA_CASE(20) DYNA_CASE(24) DYNA_CASE(28) DYNA_CASE(32)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw thread kernel: unsupported strip height %d", R);
+  }
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, const NwUnit* d_units, int num_units, int32_t* d_scratch,
+                   int max_cols, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  if (multipass) {
+    if (R != kNwWarpMaxR) return fail(DYNA_ERR_UNSUPPORTED, "nw multipass requires R=%d", kNwWarpMaxR);
+    return launch_warp_multipass(slant, d, d_units, num_units, d_scratch, max_cols, st);
+  }
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_warp_R<RR>(slant, d, d_units, num_units, st);
+    DYNA_CASE(1) DYNA_CASE(2) DYNA_CASE(3) DYNA_CASE(4) DYNA_CASE(5) DYNA_CASE(6) DYNA_CASE(7) DYNA_CASE(8)
+    DYNA_CASE(9) DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12) DYNA_CASE(13) DYNA_CASE(14) DYNA_CASE(15) DYNA_CASE(16)
+    DYNA_CASE(17) DYNA_CASE(18) DYNA_CASE(19) DYNA_CASE(20) DYNA_CASE(21) DYNA_CASE(22) DYNA_CASE(23) DYNA_CASE(24)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw warp kernel: unsupported strip height %d", R);
+  }
+}
+
+int launch_nw_expand(const uint32_t* d_matches, const uint32_t* d_length, int64_t n, int64_t row_begin, int64_t row_end,
+                     double* d_out, cudaStream_t st) {
+  if (row_end <= row_begin) return DYNA_OK;
+  const int64_t slab_base = tri_diag_rows(n, row_begin);
+  dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)std::min<int64_t>(row_end - row_begin, 32768));
+  nw_expand_kernel<<<grid, 256, 0, st>>>(d_matches, d_length, n, row_begin, row_end, slab_base, d_out);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+}  // namespace dyna

@@ -1,0 +1,48 @@
+// Needleman-Wunsch identity kernels (sm_100a): launch interface.  See nw_kernels.cu.
+#pragma once
+#include "common.cuh"
+
+namespace dyna {
+
+// A unit of work: one row sequence (the lower-index sequence, on the DP rows) against a run of
+// consecutive column sequences j_begin .. j_begin + j_count - 1 (all >= row).
+struct NwUnit {
+  int32_t row;
+  int32_t j_begin;
+  int32_t j_count;
+};
+
+struct NwDeviceData {
+  const uint8_t* codes;  // residues encoded 0..23, all sequences back to back
+  const int32_t* off;    // n+1 offsets into codes
+  const int8_t* sub;     // 24x24 substitution table, row-major [row residue][column residue]
+  int64_t n;
+  int64_t slab_base;     // packed-triangle (diagonal included) index of the plan's first pair
+  uint32_t* matches;     // outputs, slab order
+  uint32_t* length;
+  int gap_open, gap_ext;
+  uint32_t one;          // always 1; passed as data so the compiler keeps it in a register (see strip_column)
+};
+
+constexpr int kNwThreadMaxRows = 32;  // rows handled by the thread-per-pair kernel
+constexpr int kNwWarpMaxR = 24;       // rows per lane of the warp-per-pair kernel (32*24 = 768 rows per pass)
+constexpr int kNwWarpUnitPairs = 32;  // pairs per unit (8 warps x 4)
+constexpr int kNwThreadUnitPairs = 512;
+constexpr int kNwMultiPassGrid = 148 * 2;
+
+// Strip height for a row sequence of length m (m >= 1): <= 32 -> thread kernel (R = m rounded up to 4),
+// otherwise the warp kernel with R = ceil(m/32) capped at kNwWarpMaxR (longer rows take several passes).
+inline bool nw_use_thread_kernel(int m) { return m <= kNwThreadMaxRows; }
+inline int nw_thread_R(int m) { return ((m + 3) / 4) * 4; }
+inline int nw_warp_R(int m) { int r = (m + 31) / 32; return r > kNwWarpMaxR ? kNwWarpMaxR : r; }
+
+int launch_nw_empty_rows(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
+int launch_nw_thread(int R, bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
+// scratch: only for multipass (rows longer than 32*R): kNwMultiPassGrid * 8 warps * 3 * max_cols ints
+int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, const NwUnit* d_units, int num_units, int32_t* d_scratch,
+                   int max_cols, cudaStream_t st);
+// (matches, length) slab -> column-major doubles, both triangles (reference: src/pairwiseSeqAlign.cpp:311,349-350)
+int launch_nw_expand(const uint32_t* d_matches, const uint32_t* d_length, int64_t n, int64_t row_begin, int64_t row_end,
+                     double* d_out, cudaStream_t st);
+
+}  // namespace dyna

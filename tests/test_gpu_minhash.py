@@ -1,0 +1,132 @@
+"""GPU parity: MinHash kernels (through the C ABI) against the oracle, bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import dynaalign_b200 as da
+from conftest import GOLDEN, fingerprint, random_seqs, same_matrix
+from dynaalign_b200 import _lib
+from oracle import minhash_r as R
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k,n_hash", [(1, 7), (2, 50), (3, 33), (4, 500), (5, 64), (7, 129), (8, 16), (9, 20), (13, 5)])
+def test_signatures_bit_exact(k, n_hash):
+    rng = np.random.default_rng(100 + k)
+    seqs = random_seqs(rng, 60, 0, 40, "ACDEFGHIKLMNPQRSTVWY") + ["", "A", "AC", "ACDEFGHIKLMN" * 30]
+    seeds = port.hashfamily_seeds(9 + k, n_hash)
+    got = da.mh_signatures(seqs, k, seeds)
+    want = port.mh_signatures(seqs, k, seeds)
+    assert (got == want).all()
+    # sequences shorter than k keep UINT32_MAX (src/minHash.cpp:140)
+    assert (got[60] == 0xFFFFFFFF).all()
+
+
+def test_signatures_warp_reduction_path():
+    # few hash functions on long sequences take the lanes-over-windows + redux.min kernel
+    rng = np.random.default_rng(3)
+    seqs = random_seqs(rng, 20, 300, 2500, "ACDEFGHIKLMNPQRSTVWY")
+    seeds = port.hashfamily_seeds(77, 12)
+    assert (da.mh_signatures(seqs, 5, seeds) == port.mh_signatures(seqs, 5, seeds)).all()
+
+
+def test_signatures_raw_bytes_and_long_k():
+    seqs = [bytes(range(1, 200)), b"\xff\xfe\x00abc" * 9, b"lower case too", b"x"]
+    seeds = port.hashfamily_seeds(5, 40)
+    for k in (3, 4, 6, 31, 64):
+        assert (da.mh_signatures(seqs, k, seeds) == port.mh_signatures(seqs, k, seeds)).all()
+
+
+@pytest.mark.parametrize("n,n_hash", [(2, 1), (3, 50), (129, 17), (257, 500), (700, 64), (1000, 33)])
+@pytest.mark.parametrize("mode", ["tma", "ldg"])
+def test_match_counts_bit_exact(n, n_hash, mode, monkeypatch):
+    monkeypatch.setenv("DYNA_MH_MATCH", mode)
+    rng = np.random.default_rng(n * 31 + n_hash)
+    sig = rng.integers(0, 3, size=(n, n_hash), dtype=np.uint32) * np.uint32(0x9E3779B1)  # many collisions, wide values
+    sig[rng.integers(0, n, 3)] = 0xFFFFFFFF
+    assert (da.mh_match_counts(sig) == port.mh_match_counts(sig)).all()
+
+
+def test_match_counts_row_slabs():
+    rng = np.random.default_rng(8)
+    n = 900
+    sig = rng.integers(0, 5, size=(n, 100), dtype=np.uint32)
+    full = port.mh_match_counts(sig)
+    bounds = da.partition_rows(n, 5)
+    parts = [da.mh_match_counts(sig, int(bounds[s]), int(bounds[s + 1])) for s in range(5)]
+    assert (np.concatenate(parts) == full).all()
+    # unaligned row ranges
+    for a, b in [(1, 2), (127, 130), (333, 899), (899, 900), (5, 5)]:
+        assert (da.mh_match_counts(sig, a, b) == port.mh_match_counts(sig, a, b)).all()
+
+
+def test_similarityMH_evp_config1(golden, evp):
+    # BASELINE config 1: similarityMH(evp_peparray$PROBE_SEQUENCE, k=2, n_hash=50), seed injected
+    m = da.similarityMH(evp, 2, 50, seed=42)
+    assert fingerprint(m) == golden["mh_evp_k2_h50_seed42"]["fnv1a64"]
+    assert same_matrix(m, port.similarityMH(evp, 2, 50, 42))
+    sig = np.load(os.path.join(GOLDEN, "mh_evp_signatures_k2_h50_seed42.npz"))["sig"]
+    assert (da.mh_signatures(evp, 2, da.hashfamily_seeds(42, 50)) == sig).all()
+    assert (np.diag(m) == 1.0).all() and (m == m.T).all()
+
+
+def test_similarityMH_h3n2_config3_input(golden, h3n2):
+    m = da.similarityMH(h3n2, 4, 500, seed=42)
+    assert fingerprint(m) == golden["mh_h3n2_1000_k4_h500_seed42"]["fnv1a64"]
+
+
+def test_similarityMH_edge_cases():
+    # one sequence; all shorter than k (mutually identical: sim 1.0); duplicates
+    assert da.similarityMH(["ACDEF"], 4, 10, seed=1).tolist() == [[1.0]]
+    m = da.similarityMH(["AC", "A", "", "ACDEFG", "ACDEFG"], 4, 20, seed=3)
+    assert same_matrix(m, port.similarityMH(["AC", "A", "", "ACDEFG", "ACDEFG"], 4, 20, 3))
+    assert m[0, 1] == 1.0 and m[0, 2] == 1.0 and m[3, 4] == 1.0 and m[0, 3] == 0.0
+
+
+def test_similarityMH_default_seed_is_random_but_valid(evp):
+    a = da.similarityMH(evp[:50], 2, 50)
+    assert (np.diag(a) == 1.0).all() and (a == a.T).all() and ((a >= 0) & (a <= 1)).all()
+    assert np.allclose(a * 50, np.round(a * 50))
+
+
+def test_r_pipeline_on_gpu():
+    rng = np.random.default_rng(4)
+    seqs = random_seqs(rng, 40, 6, 30, "ACDEGHIKLMN")
+    vocab = R.create_vocab(seqs, 3)
+    assert da.create_vocab(seqs, 3) == vocab
+    cm = da.create_char_matrix(seqs, vocab, 3)
+    hp = R.create_hash_parameters(64, len(vocab), np.random.default_rng(5))
+    want_sig = R.compute_signature_matrix(cm, hp, len(vocab))
+    got_sig = da.compute_signature_matrix(cm, hp, len(vocab))
+    assert got_sig.shape == (64, 40) and (got_sig == want_sig).all()
+    want_d = R.compute_distance_matrix(want_sig)
+    got_d = da.compute_distance_matrix(got_sig)
+    assert same_matrix(got_d, want_d)
+    r = da.minhash(seqs, 3, 64, hash_params=hp)
+    assert same_matrix(r["dist_matrix"], want_d) and r["vocabulary"] == vocab
+    # testthat mock (tests/testthat/test-minHash.R:92-106)
+    mock = np.array([[1, 2, 3], [1, 2, 4], [2, 3, 5]], dtype=float).T
+    d = da.compute_distance_matrix(mock)
+    assert d[0, 1] == 1 - 2 / 3 and d[0, 2] == 1 and d[1, 2] == 1 and (np.diag(d) == 0).all()
+
+
+def test_linear_signatures_large_values():
+    # stay inside R's integer domain (a*x+b < 2^31) and also beyond it (64-bit on both sides)
+    rng = np.random.default_rng(6)
+    for m in (46340, 2_000_000_011):
+        n = 25
+        counts = rng.integers(0, 40, n)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        ranks = rng.integers(1, min(m, 2 ** 31 - 1), size=int(off[-1]) or 1).astype(np.int32)
+        a = rng.integers(1, m, 30).astype(np.int64)
+        b = rng.integers(0, m, 30).astype(np.int64)
+        want = port.mh_signatures_linear(ranks, off, a, b, m)
+        got = np.zeros((n, 30), dtype=np.uint32)
+        _lib.check(_lib.lib().dyna_mh_signatures_linear(_lib.ptr(ranks, C.c_int32), _lib.ptr(off, C.c_int64), n,
+                                                        _lib.ptr(a, C.c_int64), _lib.ptr(b, C.c_int64), m, 30,
+                                                        _lib.ptr(got, C.c_uint32)))
+        assert (got == want).all()

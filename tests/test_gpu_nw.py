@@ -1,0 +1,145 @@
+"""GPU parity: Needleman-Wunsch identity kernels (through the C ABI) against the oracle, bit-exact
+(matches, alignment_length) per pair and identical doubles."""
+import os
+
+import numpy as np
+import pytest
+
+import dynaalign_b200 as da
+from conftest import ALPHABET24, GOLDEN, TABLES, fingerprint, random_seqs, same_matrix
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def check_stats(seqs, name="BLOSUM62", go=10, ge=4):
+    gm, gl = da.nw_pair_stats(seqs, name, go, ge)
+    wm, wl = port.nw_pair_stats(seqs, name, go, ge)
+    bad = np.nonzero((gm != wm) | (gl != wl))[0]
+    assert bad.size == 0, "first mismatch at packed pair %d: got (%d,%d) want (%d,%d)" % (
+        bad[0], gm[bad[0]], gl[bad[0]], wm[bad[0]], wl[bad[0]])
+
+
+def test_known_answers(golden):
+    g = golden["nw_pep4"]
+    assert same_matrix(da.similarityNW(g["sequences"]), np.array(g["matrix"]))
+    o = golden["nw_order"]
+    m = da.similarityNW([o["a"], o["b"]])
+    assert m[0, 1] == o["ab"] and m[1, 0] == o["ab"]
+    m = da.similarityNW([o["b"], o["a"]])
+    assert m[0, 1] == o["ba"]  # lower index on rows: order-sensitive like the reference
+
+
+def test_empty_strings_and_nan():
+    seqs = ["", "AA", "", "ARND", "A"]
+    m = da.similarityNW(seqs)
+    assert same_matrix(m, port.similarityNW(seqs))
+    assert np.isnan(m[0, 0]) and np.isnan(m[0, 2]) and m[0, 1] == 0.0 and m[1, 1] == 1.0
+    assert np.isnan(da.similarityNW([""])[0, 0])
+
+
+@pytest.mark.parametrize("table", TABLES)
+def test_thread_kernel_short_rows(table):
+    # rows of 1..32 residues take the thread-per-pair kernel (all strip heights 4..32)
+    rng = np.random.default_rng(hash(table) % 1000)
+    seqs = random_seqs(rng, 70, 1, 32) + random_seqs(rng, 10, 33, 90) + ["", "A"]
+    rng.shuffle(seqs)
+    go, ge = int(rng.integers(0, 13)), int(rng.integers(0, 6))
+    check_stats(seqs, table, go, ge)
+
+
+@pytest.mark.parametrize("lo,hi", [(33, 64), (65, 130), (131, 260), (261, 400), (401, 600), (601, 768)])
+def test_warp_kernel_all_strip_heights(lo, hi):
+    rng = np.random.default_rng(lo)
+    seqs = random_seqs(rng, 14, lo, hi, "ARNDCQEGHILKMFPSTWYV") + random_seqs(rng, 4, 1, 40)
+    check_stats(seqs)
+
+
+def test_warp_kernel_exact_boundaries():
+    # row lengths at the strip boundaries 32*R and 32*R+1, against short and long columns
+    rng = np.random.default_rng(9)
+    lens = [32, 33, 64, 65, 96, 97, 352, 353, 384, 385, 767, 768]
+    seqs = [random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0] for L in lens] + random_seqs(rng, 3, 1, 5)
+    check_stats(seqs, "BLOSUM50", 12, 3)
+
+
+def test_multipass_long_rows():
+    rng = np.random.default_rng(10)
+    seqs = random_seqs(rng, 5, 769, 2100, "ARNDCQEGHILKMFPSTWYV") + random_seqs(rng, 4, 1, 300)
+    rng.shuffle(seqs)
+    check_stats(seqs)
+
+
+def test_similar_sequences_exercise_gaps():
+    # near-identical proteins with indels: long diagonal runs, ties and gap extensions
+    rng = np.random.default_rng(12)
+    base = random_seqs(rng, 1, 330, 330, "ARNDCQEGHILKMFPSTWYV")[0]
+    seqs = [base]
+    for _ in range(20):
+        s = list(base)
+        for _ in range(int(rng.integers(1, 12))):
+            p = int(rng.integers(0, len(s)))
+            r = rng.random()
+            if r < 0.4:
+                del s[p:p + int(rng.integers(1, 6))]
+            elif r < 0.8:
+                s[p:p] = list(random_seqs(rng, 1, 1, 5, "ARNDCQEGHILKMFPSTWYV")[0])
+            else:
+                s[p] = "W"
+        seqs.append("".join(s))
+    for name, go, ge in [("BLOSUM62", 10, 4), ("BLOSUM62", 0, 0), ("BLOSUM45", 1, 1), ("BLOSUM100", 12, 0), ("BLOSUM80", 3, 5)]:
+        check_stats(seqs, name, go, ge)
+
+
+def test_unslanted_recurrence_for_large_gap_extension():
+    # gapExt too large for the slanted int8 profile -> the explicit "- ge" kernels
+    rng = np.random.default_rng(13)
+    seqs = random_seqs(rng, 12, 1, 120, "ARNDCQEGHILKMFPSTWYV")
+    check_stats(seqs, "BLOSUM62", 30, 70)
+    check_stats(seqs, "BLOSUM62", 5, 200)
+
+
+def test_slanted_and_unslanted_agree(monkeypatch):
+    rng = np.random.default_rng(14)
+    seqs = random_seqs(rng, 20, 1, 200)
+    a = da.nw_pair_stats(seqs, "BLOSUM62", 10, 4)
+    monkeypatch.setenv("DYNA_NW_SLANT", "0")
+    b = da.nw_pair_stats(seqs, "BLOSUM62", 10, 4)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_row_range_slabs():
+    rng = np.random.default_rng(15)
+    seqs = random_seqs(rng, 60, 0, 90)
+    wm, wl = port.nw_pair_stats(seqs)
+    lens = [len(s) for s in seqs]
+    bounds = da.partition_rows(len(seqs), 4, weights=lens, include_diagonal=True)
+    gm = np.concatenate([da.nw_pair_stats(seqs, row_begin=int(bounds[s]), row_end=int(bounds[s + 1]))[0] for s in range(4)])
+    gl = np.concatenate([da.nw_pair_stats(seqs, row_begin=int(bounds[s]), row_end=int(bounds[s + 1]))[1] for s in range(4)])
+    assert (gm == wm).all() and (gl == wl).all()
+
+
+def test_evp_full_matrix_fingerprint(golden, evp):
+    m = da.similarityNW(evp)
+    assert fingerprint(m) == golden["nw_evp_blosum62_10_4"]["fnv1a64"]
+    for key, fp in golden.items():
+        if key.startswith("nw_evp40_"):
+            _, _, nm, go, ge = key.split("_")
+            assert fingerprint(da.similarityNW(evp[:40], nm, int(go), int(ge))) == fp["fnv1a64"], key
+
+
+def test_h3n2_first24(golden, h3n2):
+    m = da.similarityNW(h3n2[:24])
+    assert fingerprint(m) == golden["nw_h3n2_24"]["fnv1a64"]
+    assert same_matrix(m, np.array(golden["nw_h3n2_24"]["matrix"]))
+
+
+def test_h3n2_config2_full(golden, h3n2):
+    # BASELINE config 2: similarityNW(h3n2sample$sequence[1:1000]); golden (matches, length) for all 500,500 pairs
+    g = np.load(os.path.join(GOLDEN, "nw_h3n2_1000_stats.npz"))
+    gm, gl = da.nw_pair_stats(h3n2)
+    assert (gm == g["matches"]).all() and (gl == g["length"]).all()
+    m = da.similarityNW(h3n2)
+    assert (m == m.T).all() and (np.diag(m) == 1.0).all()
+    for s in golden["nw_h3n2_1000_sample"]:
+        assert m[s["i"], s["j"]] == s["sim"]
