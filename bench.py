@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DynaAlign all-pairs similarity hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): NW all-pairs GCUPS and MinHash pairs/s.  One JSON line on stdout (rank 0):
+
+  * headline `metric` = nw_allpairs_gcups on BASELINE config 5 (synthetic 20k proteins of ~330 aa, BLOSUM62 10/4,
+    all pairs i<=j, row blocks balanced by DP cells over the ranks);  a step = one pass over the whole workload.
+  * `minhash` sub-object = minhash_pairs_per_sec on config 4 (synthetic 100k peptides of 16 aa, k=4, n_hash=500),
+    with its own value / e2e / roofline.
+  * `value`: inputs already resident in HBM (device plans), CUDA events on the launching stream, max over ranks.
+  * `e2e`: the same work through the host C ABI (dyna_nw_pair_stats / plan upload+run+fetch): pinned host buffers,
+    H2D + D2H inside the timed region.
+  * `roofline`: for the dominant kernel (nw_warp_kernel): algorithmic integer ops (11 per DP cell)
+    per second against the INT32 issue peak measured live with dyna_probe_int_issue (MEASURED_PEAKS.json has no
+    integer figure).  The MinHash match kernel reports the HBM roofline BASELINE.json names (2.04 B/pair) and the
+    integer one that actually binds it.
+  * `cpu_baseline` (N=1, rank 0): the reference's own C++ (oracle/_ref, compiled unmodified) timed on a bounded
+    sample of the same workloads on the box's host cores.
+
+`--impl reference` times that CPU reference alone on the same metric (rank 0 only under torchrun).
+Scaling is STRONG: the workload is fixed and sharded, so per-GPU work shrinks as N grows.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NW_OPS_PER_CELL = 11.0        # algorithmic integer instructions per DP cell
+MH_BYTES_PER_PAIR = 2.0       # one u16 match count per unordered pair (+ 4*N*n_hash signature bytes, added below)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=float(max(power)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- workloads
+def nw_workload(n):
+    from dynaalign_b200 import synth
+    return synth.proteins_families(n)
+
+
+def mh_workload(n):
+    from dynaalign_b200 import synth
+    return synth.peptides_uniform(n)
+
+
+# --------------------------------------------------------------------------------------------- reference (CPU) arm
+def reference_backend():
+    """(module, kind): the compiled reference when it travelled with the repo, else the C port of it."""
+    from oracle import port, ref
+    if ref.available():
+        return ref, "reference"
+    return port, "port"
+
+
+def cpu_nw_sample(seqs, n_sample):
+    """Reference similarityNW (single-threaded by construction) on the first n_sample sequences -> (GCUPS, seconds)."""
+    mod, kind = reference_backend()
+    sub = seqs[:n_sample]
+    lens = np.array([len(s) for s in sub], dtype=np.int64)
+    suffix = np.cumsum(lens[::-1])[::-1]
+    cells = int((lens * suffix).sum())
+    t0 = time.perf_counter()
+    mod.similarityNW(sub, "BLOSUM62", 10, 4)
+    dt = time.perf_counter() - t0
+    return cells / dt / 1e9, dt, cells, kind
+
+
+def cpu_mh_sample(seqs, n_sample, threads):
+    mod, kind = reference_backend()
+    sub = seqs[:n_sample]
+    if kind == "reference":
+        mod.set_threads(threads)
+    else:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    t0 = time.perf_counter()
+    mod.similarityMH(sub, 4, 500, 42)
+    dt = time.perf_counter() - t0
+    pairs = n_sample * (n_sample - 1) // 2
+    return pairs / dt, dt, pairs, kind
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    seqs = nw_workload(min(args.nw_n, 256))
+    n_sample = 48
+    times = []
+    cells = kind = None
+    for it in range(args.warmup + args.steps):
+        gc, dt, cells, kind = cpu_nw_sample(seqs, n_sample)
+        if it >= args.warmup:
+            times.append(dt)
+    dt = float(np.mean(times))
+    value = cells / dt / 1e9
+    peps = mh_workload(4000)
+    cores = os.cpu_count() or 1
+    mh_rate, mh_dt, mh_pairs, _ = cpu_mh_sample(peps, 4000, cores)
+    line = {
+        "impl": "reference", "metric": "nw_allpairs_gcups", "value": value, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "similarityNW BLOSUM62 10/4, synthetic %d proteins ~330 aa (config 5); reference timed on the "
+                               "first %d sequences per step" % (args.nw_n, n_sample)},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": 1, "kind": kind,
+                         "sample": "first %d sequences of config 5 (%d pairs, %.3g cells) per step; similarityNW is "
+                                   "single-threaded in the reference" % (n_sample, n_sample * (n_sample + 1) // 2, cells)},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "minhash": {"metric": "minhash_pairs_per_sec", "value": mh_rate, "unit": "pairs/s", "cores": cores,
+                    "sample": "first 4000 peptides of config 4 (%d pairs), k=4 n_hash=500, signature build included" % mh_pairs},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--nw-n", type=int, default=20000, help="config 5 size (development: smaller)")
+    ap.add_argument("--mh-n", type=int, default=100000, help="config 4 size (development: smaller)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from dynaalign_b200 import _lib
+    from dynaalign_b200._lib import check, flatten, lib, ptr
+
+    L = lib()
+    if L.dyna_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    stream = torch.cuda.current_stream()
+    st = C.c_void_p(stream.cuda_stream)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = vis.split(",")[local_rank] if vis else str(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def timed_steps(fn, warmup, steps):
+        """K steps, each bracketed by events on the launching stream; L2 flushed between steps (outside the events)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for k in range(steps):
+            flush_buf.fill_(k)
+            e0[k].record(stream)
+            fn()
+            e1[k].record(stream)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+        return max_over_ranks(ms)
+
+    # ---------------- integer issue peak (roofline denominator), measured live on this device
+    peak_ops, peak_ms = C.c_double(0), C.c_double(0)
+    check(L.dyna_probe_int_issue(0, C.byref(peak_ops), C.byref(peak_ms), st))
+    int_peak = peak_ops.value  # lane-ops/s
+
+    sampler = ClockSampler(phys)
+    launches = 0
+
+    # ================================================================== NW, config 5
+    seqs = nw_workload(args.nw_n)
+    n = len(seqs)
+    res, off = flatten(seqs)
+    lens = np.diff(off)
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    check(L.dyna_partition_rows(n, ptr(lens.astype(np.int64), C.c_int64), 1, world, ptr(bounds, C.c_int64)))
+    rb, re_ = int(bounds[rank]), int(bounds[rank + 1])
+    plan = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, rb, re_, dev)
+    if not plan:
+        raise SystemExit("bench.py: " + _lib.last_error())
+    my_cells = L.dyna_nw_plan_cells(plan)
+    my_pairs = L.dyna_nw_plan_pairs(plan)
+    total_cells = sum_over_ranks(my_cells)
+    total_pairs = sum_over_ranks(my_pairs)
+
+    sampler.start()
+    nw_ms = timed_steps(lambda: check(L.dyna_nw_plan_run(plan, st)), args.warmup, args.steps)
+    clocks = sampler.stop()
+    nw_launch_per_step = L.dyna_nw_plan_launches(plan)
+    launches += nw_launch_per_step * args.steps
+    nw_ms_per_step = nw_ms / args.steps
+    nw_gcups = total_cells / (nw_ms_per_step * 1e-3) / 1e9
+    L.dyna_nw_plan_destroy(plan)
+
+    # e2e: host C ABI with pinned host buffers, H2D + D2H inside the timed region
+    pin_res = torch.from_numpy(res).pin_memory()
+    pin_off = torch.from_numpy(off).pin_memory()
+    out_m = torch.empty(max(my_pairs, 1), dtype=torch.int32).pin_memory()
+    out_l = torch.empty(max(my_pairs, 1), dtype=torch.int32).pin_memory()
+    check(L.dyna_set_device(dev))
+
+    def nw_e2e_step():
+        check(L.dyna_nw_pair_stats(C.cast(pin_res.data_ptr(), C.POINTER(C.c_uint8)), C.cast(pin_off.data_ptr(), C.POINTER(C.c_int64)),
+                                   n, b"BLOSUM62", 10, 4, rb, re_, C.cast(out_m.data_ptr(), C.POINTER(C.c_uint32)),
+                                   C.cast(out_l.data_ptr(), C.POINTER(C.c_uint32))))
+
+    nw_e2e_step()  # warm-up (allocator, first touch)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        nw_e2e_step()
+    barrier()
+    nw_e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    nw_e2e_gcups = total_cells / nw_e2e_s / 1e9
+    launches += nw_launch_per_step * (e2e_steps + 1)
+    # sanity: self-alignment of the first row of this rank's slab is an identity (matches == length == len)
+    if my_pairs > 0:
+        assert int(out_m[0]) == int(lens[rb]) and int(out_l[0]) == int(lens[rb]), "NW e2e sanity check failed"
+    nw_h2d = int(res.nbytes + off.nbytes)
+    nw_d2h = int(8 * my_pairs)
+    del out_m, out_l, pin_res, pin_off
+
+    # ================================================================== MinHash, config 4
+    peps = mh_workload(args.mh_n)
+    mn, n_hash, k = len(peps), 500, 4
+    mres, moff = flatten(peps)
+    seeds = np.zeros(n_hash, dtype=np.uint32)
+    check(L.dyna_hashfamily_seeds(42, n_hash, ptr(seeds, C.c_uint32)))
+    mb = np.zeros(world + 1, dtype=np.int64)
+    check(L.dyna_partition_rows(mn, None, 0, world, ptr(mb, C.c_int64)))
+    mrb, mre = int(mb[rank]), int(mb[rank + 1])
+    mplan = L.dyna_mh_plan_create(mn, n_hash, mrb, mre, dev)
+    if not mplan:
+        raise SystemExit("bench.py: " + _lib.last_error())
+    mh_my_pairs = L.dyna_mh_plan_pairs(mplan)
+    mh_total_pairs = sum_over_ranks(mh_my_pairs)
+    check(L.dyna_mh_plan_upload_sequences(mplan, ptr(mres, C.c_uint8), ptr(moff, C.c_int64), k, ptr(seeds, C.c_uint32), st))
+
+    def mh_step():
+        check(L.dyna_mh_plan_run_signatures(mplan, st))
+        check(L.dyna_mh_plan_run_match(mplan, st))
+
+    mh_ms = timed_steps(mh_step, max(args.warmup, 3), max(args.steps, 3)) / max(args.steps, 3)
+    launches += 3 * max(args.steps, 3)
+    # match kernel alone (the roofline kernel of this half)
+    check(L.dyna_mh_plan_run_signatures(mplan, st))
+    mh_match_ms = timed_steps(lambda: check(L.dyna_mh_plan_run_match(mplan, st)), 1, 3) / 3
+    launches += 3
+    mh_pairs_s = mh_total_pairs / (mh_ms * 1e-3)
+
+    # e2e: upload sequences, signatures, match, counts slab back to pinned host memory
+    pin_counts = torch.empty(max(mh_my_pairs, 1), dtype=torch.int16).pin_memory()
+    pin_mres = torch.from_numpy(mres).pin_memory()
+    pin_moff = torch.from_numpy(moff).pin_memory()
+
+    def mh_e2e_step():
+        check(L.dyna_mh_plan_upload_sequences(mplan, C.cast(pin_mres.data_ptr(), C.POINTER(C.c_uint8)),
+                                              C.cast(pin_moff.data_ptr(), C.POINTER(C.c_int64)), k, ptr(seeds, C.c_uint32), st))
+        check(L.dyna_mh_plan_run_signatures(mplan, st))
+        check(L.dyna_mh_plan_run_match(mplan, st))
+        check(L.dyna_mh_plan_fetch_counts(mplan, C.cast(pin_counts.data_ptr(), C.POINTER(C.c_uint16)), st))
+
+    mh_e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        mh_e2e_step()
+    barrier()
+    mh_e2e_s = max_over_ranks((time.perf_counter() - t0) / 3)
+    launches += 3 * 4
+    L.dyna_mh_plan_destroy(mplan)
+    mh_alg_bytes = MH_BYTES_PER_PAIR * mh_total_pairs + 4.0 * mn * n_hash * world  # every rank reads all signatures once
+
+    # ================================================================== CPU baseline (rank 0, N=1)
+    cpu = None
+    cpu_mh = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        gc, dt, cells, kind = cpu_nw_sample(seqs, 48)
+        cpu = {"value": gc, "unit": "GCUPS", "cores": 1, "kind": kind,
+               "sample": "reference similarityNW on the first 48 sequences of config 5 (1176 pairs, %.3g cells, %.1f s); "
+                         "the reference NW is single-threaded" % (cells, dt)}
+        cores = os.cpu_count() or 1
+        rate, dt, pairs, kind = cpu_mh_sample(peps, 4000, cores)
+        cpu_mh = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
+                  "sample": "reference similarityMH on the first 4000 peptides of config 4 (%d pairs, %.1f s), OpenMP on all host cores" % (pairs, dt)}
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    tinfo = {}
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tinfo = json.load(f)
+        traffic = tinfo.get("nw_warp_kernel_dram_bytes_per_launch")
+
+    if rank == 0:
+        achieved = NW_OPS_PER_CELL * total_cells / (nw_ms_per_step * 1e-3) / world  # per GPU
+        line = {
+            "metric": "nw_allpairs_gcups", "value": nw_gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": nw_ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "similarityNW BLOSUM62 gapOpen=10 gapExt=4 on synthetic %d proteins of ~330 aa (BASELINE config 5), "
+                                   "all %d pairs i<=j = %.4g DP cells per step; row blocks balanced by cells over %d rank(s)"
+                                   % (n, int(total_pairs), total_cells, world),
+                       "l2": "256 MB flush write between timed steps; NW inputs (6.6 MB) are L2-resident by nature, outputs 8 B/pair",
+                       "timing": "per-step CUDA events on the launching stream, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": nw_e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": nw_h2d, "d2h_bytes_per_step": nw_d2h,
+                    "api": "dyna_nw_pair_stats (validate + encode + plan + H2D + kernels + D2H), pinned host buffers"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "int32_issue", "achieved": achieved / 1e9, "peak": int_peak / 1e9, "unit": "Gop/s",
+                         "frac": achieved / int_peak, "traffic": traffic,
+                         "note": "dominant kernel nw_warp_kernel: neither HBM- nor tensor-bound; 11 algorithmic integer ops per DP cell "
+                                 "(SURVEY.md 8(d)) against the INT32 issue peak measured live by dyna_probe_int_issue (IADD3 chains)"},
+            "cpu_baseline": cpu,
+            "minhash": {
+                "metric": "minhash_pairs_per_sec", "value": mh_pairs_s, "unit": "pairs/s", "ms_per_step": mh_ms,
+                "config": {"workload": "similarityMH k=4 n_hash=500 on synthetic %d peptides of 16 aa (BASELINE config 4), %d pairs per step; "
+                                       "signatures rebuilt every step; u16 match counts for the strict upper triangle stay in HBM"
+                                       % (mn, int(mh_total_pairs)),
+                           "l2": "inputs (2 x %.0f MB signatures) and the %.1f GB output exceed the 126 MB L2" % (4.0 * mn * mh_hrows(n_hash) / 1e6, 2.0 * mh_total_pairs / 1e9)},
+                "e2e": {"value": mh_total_pairs / mh_e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(mres.nbytes + moff.nbytes + seeds.nbytes),
+                        "d2h_bytes_per_step": int(2 * mh_my_pairs), "api": "dyna_mh_plan_upload_sequences + run_signatures + run_match + fetch_counts"},
+                "roofline": {"bound": "hbm", "achieved": mh_alg_bytes / world / (mh_match_ms * 1e-3) / 1e9,
+                             "peak": peaks_hbm(), "unit": "GB/s",
+                             "frac": mh_alg_bytes / world / (mh_match_ms * 1e-3) / 1e9 / peaks_hbm(),
+                             "traffic": tinfo.get("mh_match_kernel_dram_bytes_per_launch"),
+                             "note": "BASELINE names the HBM roofline (2 B/pair + signatures, peak = measured hbm_gbs); the kernel is "
+                                     "integer-issue-bound by construction (n_hash compares per pair), see int32_issue_frac"},
+                "match_kernel_ms": mh_match_ms,
+                "int32_issue_frac": 1.5 * n_hash * mh_total_pairs / world / (mh_match_ms * 1e-3) / int_peak,
+                "cpu_baseline": cpu_mh,
+            },
+            "int32_issue_peak_lane_ops_per_s": int_peak,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def mh_hrows(n_hash):
+    return ((n_hash + 15) // 16) * 16
+
+
+def peaks_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f).get("hbm_gbs", 6650.0))
+    return 6650.0  # fallback stated in B200_PROFILING.md
+
+
+if __name__ == "__main__":
+    main()

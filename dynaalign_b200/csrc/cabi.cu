@@ -121,7 +121,7 @@ struct dyna_mh_plan {
   int launches = 0;
   DevBuf<uint8_t> res;
   DevBuf<int64_t> off;
-  DevBuf<uint32_t> seeds, sig, sigT, sigTneg;
+  DevBuf<uint32_t> seeds, sig, sigT;
   DevBuf<uint16_t> counts;
   bool have_sequences = false, have_sig = false, have_sigT = false;
 };
@@ -141,8 +141,7 @@ extern "C" dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_
   p->row_begin = row_begin;
   p->row_end = row_end;
   p->pairs = tri_strict_rows(n, row_end) - tri_strict_rows(n, row_begin);
-  if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch) ||
-      p->sigTneg.alloc((size_t)p->hrows * p->npitch) || p->counts.alloc((size_t)p->pairs))
+  if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch) || p->counts.alloc((size_t)p->pairs))
     return nullptr;
   return p.release();
 }
@@ -174,7 +173,7 @@ extern "C" int dyna_mh_plan_upload_signatures(dyna_mh_plan* p, const uint32_t* s
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DYNA_CUDA(cudaMemcpyAsync(p->sig.p, sig, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyHostToDevice, st));
-  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->sigTneg.p, p->npitch, p->hrows, st));
+  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->npitch, p->hrows, st));
   p->have_sig = p->have_sigT = true;
   p->launches = 1;
   return DYNA_OK;
@@ -186,7 +185,7 @@ extern "C" int dyna_mh_plan_run_signatures(dyna_mh_plan* p, void* stream) {
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
-  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->sigTneg.p, p->npitch, p->hrows, st));
+  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->npitch, p->hrows, st));
   p->have_sig = p->have_sigT = true;
   p->launches = 2;
   return DYNA_OK;
@@ -198,7 +197,7 @@ extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int l = 0;
-  DYNA_TRY(launch_mh_match(p->sigT.p, p->sigTneg.p, p->npitch, p->hrows, p->n, p->row_begin, p->row_end, p->counts.p, st, &l));
+  DYNA_TRY(launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, p->row_begin, p->row_end, p->counts.p, st, &l));
   p->launches = l;
   return DYNA_OK;
 }

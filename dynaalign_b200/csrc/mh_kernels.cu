@@ -193,12 +193,12 @@ mh_signature_linear_kernel(const int32_t* __restrict__ ranks, const int64_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// layout: sig[n][n_hash] -> hash-major sigT[hrows][npitch] and its negation sigTneg (0 - x).
-// Padding hash rows (h >= n_hash) hold 0 in sigT and 1 in sigTneg so that they always MISmatch;
-// padding columns (i >= n) are zero in both and never stored by the match kernel.
+// layout: sig[n][n_hash] -> hash-major sigT[hrows][npitch].  Padding hash rows (h >= n_hash) and padding
+// columns (i >= n) are zero; padded hash rows therefore match for every pair and the match kernel subtracts
+// (hrows - n_hash) before storing, padded columns are never stored.
 // ------------------------------------------------------------------------------------------------
 __global__ void mh_transpose_kernel(const uint32_t* __restrict__ sig, int64_t n, int n_hash, uint32_t* __restrict__ sigT,
-                                    uint32_t* __restrict__ sigTneg, int64_t npitch, int hrows) {
+                                    int64_t npitch, int hrows) {
   __shared__ uint32_t tile[32][33];
   const int64_t i0 = (int64_t)blockIdx.x * 32;  // sequence block
   const int h0 = blockIdx.y * 32;               // hash block
@@ -212,9 +212,7 @@ __global__ void mh_transpose_kernel(const uint32_t* __restrict__ sig, int64_t n,
     const int h = h0 + r;
     const int64_t i = i0 + threadIdx.x;
     if (h < hrows && i < npitch) {
-      const uint32_t v = tile[threadIdx.x][r];
-      sigT[(int64_t)h * npitch + i] = v;
-      sigTneg[(int64_t)h * npitch + i] = (h < n_hash) ? (0u - v) : 1u;
+      sigT[(int64_t)h * npitch + i] = tile[threadIdx.x][r];
     }
   }
 }
@@ -224,12 +222,10 @@ __global__ void mh_transpose_kernel(const uint32_t* __restrict__ sig, int64_t n,
 //
 // A CTA owns a 128 x 128 tile of pairs; each of its 256 threads owns 8 x 8 pairs and walks the hash
 // dimension in stages of kMatchBK components staged in shared memory as [h][sequence] (so a thread's
-// 4-wide groups are single 128-bit LDS, A-side reads broadcast across the half-warp).
+// 4-wide groups are single 128-bit LDS, A-side reads broadcast across the half-warp).  Tiles are aligned
+// to 128 sequences globally; rows and columns of a tile are two boxes of the same hash-major tensor.
 //
-// Inner op: the kernel counts MISmatches with DPX, ne += min(a + (-b), 1) -- one VIADDMNMX.U32 per
-// compare plus one 3-input IADD3 per two compares (1.5 issue slots per compare; the naive
-// `cnt += (a == b)` compiles to 3) -- and stores matches = hrows - ne.  The negated operand comes
-// from the sigTneg copy, so no per-element negate is issued.
+// Inner op: see count_eq() -- 2 issue slots per compare, split over both integer pipes.
 //
 // Two loaders feed the same compute core:
 //   * TMA (default): cp.async.bulk.tensor 2-D boxes {128 sequences, kMatchBK hashes} into a 3-stage
@@ -243,7 +239,7 @@ constexpr uint32_t kStageBytes = 2u * kMatchBK * kMatchBM * sizeof(uint32_t);
 
 struct __align__(128) MatchStage {
   uint32_t a[kMatchBK][kMatchBM];
-  uint32_t b[kMatchBK][kMatchBN];  // negated
+  uint32_t b[kMatchBK][kMatchBN];
 };
 
 // tile id -> (tile row a, tile col b); tile row a has (T0 - a) tiles, b = 0 is the diagonal tile
@@ -257,40 +253,42 @@ __device__ __forceinline__ void tile_from_id(int64_t t, int64_t T0, int64_t& a, 
   b = t - (aa * T0 - aa * (aa - 1) / 2);
 }
 
-__device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty, int tx, uint32_t (&ne)[8][8]) {
+// one equality compare + count: ISETP.EQ on the ALU pipe, predicated add on the other integer pipe, so the two
+// 16-lane pipes of an SM sub-partition run side by side (measured: 63 compares/clk/SM for this pair vs 43 for the
+// DPX min(a-b,1) form and 32 for the compiler's own `cnt += (a == b)` lowering).  Pinned with PTX because nvcc
+// otherwise turns the increment into an unconditional add plus a predicated move (3 issue slots).
+__device__ __forceinline__ void count_eq(uint32_t& cnt, uint32_t a, uint32_t b) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(cnt) : "r"(a), "r"(b));
+}
+
+__device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty, int tx, uint32_t (&cnt)[8][8]) {
 #pragma unroll
-  for (int hh = 0; hh < kMatchBK; hh += 2) {
-    uint32_t av[2][8], bv[2][8];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh + u][ty * 4]);
-      const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh + u][64 + ty * 4]);
-      const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh + u][tx * 4]);
-      const uint4 b1 = *reinterpret_cast<const uint4*>(&st.b[hh + u][64 + tx * 4]);
-      av[u][0] = a0.x; av[u][1] = a0.y; av[u][2] = a0.z; av[u][3] = a0.w;
-      av[u][4] = a1.x; av[u][5] = a1.y; av[u][6] = a1.z; av[u][7] = a1.w;
-      bv[u][0] = b0.x; bv[u][1] = b0.y; bv[u][2] = b0.z; bv[u][3] = b0.w;
-      bv[u][4] = b1.x; bv[u][5] = b1.y; bv[u][6] = b1.z; bv[u][7] = b1.w;
-    }
+  for (int hh = 0; hh < kMatchBK; ++hh) {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh][ty * 4]);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh][64 + ty * 4]);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh][tx * 4]);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(&st.b[hh][64 + tx * 4]);
+    const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        ne[i][j] += __viaddmin_u32(av[0][i], bv[0][j], 1u) + __viaddmin_u32(av[1][i], bv[1][j], 1u);
+      for (int j = 0; j < 8; ++j) count_eq(cnt[i][j], av[i], bv[j]);
   }
 }
 
 // counts tile -> packed strict upper triangle, staged through shared memory for coalesced rows
-__device__ __forceinline__ void match_store_tile(uint16_t (*cs)[kCsPitch], const uint32_t (&ne)[8][8], int hrows, int ty,
+__device__ __forceinline__ void match_store_tile(uint16_t (*cs)[kCsPitch], const uint32_t (&ne)[8][8], int pad, int ty,
                                                  int tx, int lx, int lw, int64_t r0, int64_t c0, int64_t n,
-                                                 int64_t row_end, int64_t slab_base, uint16_t* __restrict__ counts) {
+                                                 int64_t row_begin, int64_t row_end, int64_t slab_base,
+                                                 uint16_t* __restrict__ counts) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int ri = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cj = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
-      cs[ri][cj] = (uint16_t)((uint32_t)hrows - ne[i][j]);
+      cs[ri][cj] = (uint16_t)(ne[i][j] - (uint32_t)pad);
     }
   }
   __syncthreads();
@@ -298,6 +296,7 @@ __device__ __forceinline__ void match_store_tile(uint16_t (*cs)[kCsPitch], const
   for (int r = lw; r < kMatchBM; r += kMatchThreads / 32) {
     const int64_t i = r0 + r;
     if (i >= row_end) break;
+    if (i < row_begin) continue;  // tiles are 128-aligned globally; the first tile row may start before the slab
     const int64_t rowbase = i * n - i * (i + 1) / 2 - i - 1 - slab_base;  // + j
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -342,13 +341,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
 }
 
 struct TmapPair {
-  alignas(64) unsigned char a[128];  // CUtensorMap over sigT
-  alignas(64) unsigned char b[128];  // CUtensorMap over sigTneg
+  alignas(64) unsigned char a[128];  // CUtensorMap over sigT (rows and columns of a tile read the same tensor)
 };
 
 __global__ void __launch_bounds__(kMatchThreads, 2)
-mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int64_t n, int64_t row_begin, int64_t row_end,
-                    uint16_t* __restrict__ counts, int64_t slab_base, int64_t T0, int64_t num_tiles) {
+mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int n_hash, int64_t n, int64_t tile_base, int64_t row_begin,
+                    int64_t row_end, uint16_t* __restrict__ counts, int64_t slab_base, int64_t T0, int64_t num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MatchStage* stages = reinterpret_cast<MatchStage*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kMatchStages * sizeof(MatchStage));
@@ -369,7 +367,7 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int64_t n, i
   for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
     int64_t ta, tb;
     tile_from_id(t, T0, ta, tb);
-    const int64_t r0 = row_begin + ta * kMatchBM;
+    const int64_t r0 = tile_base + ta * kMatchBM;
     const int64_t c0 = r0 + tb * kMatchBN;
 
     uint32_t ne[8][8];
@@ -381,7 +379,7 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int64_t n, i
     auto issue = [&](int kb, uint32_t slot) {
       mbar_expect_tx(&full[slot], kStageBytes);
       tma_load_2d(&stages[slot].a[0][0], tm.a, (int)r0, kb * kMatchBK, &full[slot]);
-      tma_load_2d(&stages[slot].b[0][0], tm.b, (int)c0, kb * kMatchBK, &full[slot]);
+      tma_load_2d(&stages[slot].b[0][0], tm.a, (int)c0, kb * kMatchBK, &full[slot]);
     };
     if (tid == 0) {
       // generic-proxy writes of the previous tile's staging (cs) must be ordered before async-proxy writes
@@ -395,15 +393,15 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int64_t n, i
       match_stage_compute(stages[slot], ty, tx, ne);
       __syncthreads();  // slot free for the load issued at the top of the next iteration
     }
-    match_store_tile(cs, ne, hrows, ty, tx, lx, lw, r0, c0, n, row_end, slab_base, counts);
+    match_store_tile(cs, ne, hrows - n_hash, ty, tx, lx, lw, r0, c0, n, row_begin, row_end, slab_base, counts);
     __syncthreads();  // cs (aliasing the ring) fully read before the next tile's loads land
   }
 }
 
 __global__ void __launch_bounds__(kMatchThreads, 2)
-mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, const uint32_t* __restrict__ sigTneg, int64_t npitch, int hrows,
-                    int64_t n, int64_t row_begin, int64_t row_end, uint16_t* __restrict__ counts, int64_t slab_base,
-                    int64_t T0, int64_t num_tiles) {
+mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, int64_t npitch, int hrows, int n_hash,
+                    int64_t n, int64_t tile_base, int64_t row_begin, int64_t row_end, uint16_t* __restrict__ counts,
+                    int64_t slab_base, int64_t T0, int64_t num_tiles) {
   __shared__ __align__(128) unsigned char smem_raw[(sizeof(MatchStage) > sizeof(uint16_t) * kMatchBM * kCsPitch)
                                                        ? sizeof(MatchStage)
                                                        : sizeof(uint16_t) * kMatchBM * kCsPitch];
@@ -417,7 +415,7 @@ mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, const uint32_t* __restric
   for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
     int64_t ta, tb;
     tile_from_id(t, T0, ta, tb);
-    const int64_t r0 = row_begin + ta * kMatchBM;
+    const int64_t r0 = tile_base + ta * kMatchBM;
     const int64_t c0 = r0 + tb * kMatchBN;
     uint32_t ne[8][8];
 #pragma unroll
@@ -433,7 +431,7 @@ mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, const uint32_t* __restric
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           pa[q][v] = __ldg(sigT + rowoff + r0 + lx + 32 * v);
-          pb[q][v] = __ldg(sigTneg + rowoff + c0 + lx + 32 * v);
+          pb[q][v] = __ldg(sigT + rowoff + c0 + lx + 32 * v);
         }
       }
     };
@@ -452,7 +450,7 @@ mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, const uint32_t* __restric
       match_stage_compute(st, ty, tx, ne);
     }
     __syncthreads();
-    match_store_tile(cs, ne, hrows, ty, tx, lx, lw, r0, c0, n, row_end, slab_base, counts);
+    match_store_tile(cs, ne, hrows - n_hash, ty, tx, lx, lw, r0, c0, n, row_begin, row_end, slab_base, counts);
   }
 }
 
@@ -507,11 +505,11 @@ int launch_mh_signature_linear(const int32_t* d_ranks, const int64_t* d_roff, in
   return DYNA_OK;
 }
 
-int launch_mh_transpose(const uint32_t* d_sig, int64_t n, int n_hash, uint32_t* d_sigT, uint32_t* d_sigTneg,
-                        int64_t npitch, int hrows, cudaStream_t st) {
+int launch_mh_transpose(const uint32_t* d_sig, int64_t n, int n_hash, uint32_t* d_sigT, int64_t npitch, int hrows,
+                        cudaStream_t st) {
   dim3 grid((unsigned)((npitch + 31) / 32), (unsigned)((hrows + 31) / 32));
   dim3 block(32, 8);
-  mh_transpose_kernel<<<grid, block, 0, st>>>(d_sig, n, n_hash, d_sigT, d_sigTneg, npitch, hrows);
+  mh_transpose_kernel<<<grid, block, 0, st>>>(d_sig, n, n_hash, d_sigT, npitch, hrows);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }
@@ -546,24 +544,26 @@ static int encode_sig_tmap(void* out128, const uint32_t* base, int64_t npitch, i
   return DYNA_OK;
 }
 
-int launch_mh_match(const uint32_t* d_sigT, const uint32_t* d_sigTneg, int64_t npitch, int hrows, int64_t n,
-                    int64_t row_begin, int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches) {
+int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_hash, int64_t n, int64_t row_begin,
+                    int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches) {
   if (launches) *launches = 0;
   if (row_end <= row_begin || n < 2) return DYNA_OK;
-  const int64_t T0 = (n - row_begin + kMatchBM - 1) / kMatchBM;
-  const int64_t NA = (row_end - row_begin + kMatchBM - 1) / kMatchBM;
+  // tiles are aligned to 128 sequences globally (TMA box origins must be 16-byte aligned); rows of the first tile
+  // row that precede row_begin are computed but not stored
+  const int64_t tile_base = (row_begin / kMatchBM) * kMatchBM;
+  const int64_t T0 = (n - tile_base + kMatchBM - 1) / kMatchBM;
+  const int64_t NA = (row_end - tile_base + kMatchBM - 1) / kMatchBM;
   const int64_t num_tiles = NA * T0 - NA * (NA - 1) / 2;
   const int64_t slab_base = tri_strict_rows(n, row_begin);
   const int grid = (int)std::min<int64_t>(num_tiles, (int64_t)kNumSMsB200 * 2);
   const char* mode = getenv("DYNA_MH_MATCH");
   if (mode && strcmp(mode, "ldg") == 0) {
-    mh_match_ldg_kernel<<<grid, kMatchThreads, 0, st>>>(d_sigT, d_sigTneg, npitch, hrows, n, row_begin, row_end,
+    mh_match_ldg_kernel<<<grid, kMatchThreads, 0, st>>>(d_sigT, npitch, hrows, n_hash, n, tile_base, row_begin, row_end,
                                                         d_counts, slab_base, T0, num_tiles);
   } else {
     if (npitch >= (1ll << 31)) return fail(DYNA_ERR_UNSUPPORTED, "too many sequences for the TMA match kernel");
     TmapPair tm;
     DYNA_TRY(encode_sig_tmap(tm.a, d_sigT, npitch, hrows));
-    DYNA_TRY(encode_sig_tmap(tm.b, d_sigTneg, npitch, hrows));
     const size_t smem = kMatchStages * sizeof(MatchStage) + kMatchStages * sizeof(uint64_t);
     static_assert(kMatchStages * sizeof(MatchStage) >= sizeof(uint16_t) * kMatchBM * kCsPitch, "staging tile must fit the ring");
     static bool attr_done = false;
@@ -571,7 +571,7 @@ int launch_mh_match(const uint32_t* d_sigT, const uint32_t* d_sigTneg, int64_t n
       DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done = true;
     }
-    mh_match_tma_kernel<<<grid, kMatchThreads, smem, st>>>(tm, hrows, n, row_begin, row_end, d_counts, slab_base, T0,
+    mh_match_tma_kernel<<<grid, kMatchThreads, smem, st>>>(tm, hrows, n_hash, n, tile_base, row_begin, row_end, d_counts, slab_base, T0,
                                                            num_tiles);
   }
   DYNA_CUDA(cudaGetLastError());

@@ -20,12 +20,12 @@ int launch_mh_signature_murmur3(const uint8_t* d_res, const int64_t* d_off, int6
 // K2: signatures from vocabulary ranks with (a*x+b) mod m (R/minHash.R:104-106,126-143)
 int launch_mh_signature_linear(const int32_t* d_ranks, const int64_t* d_roff, int64_t n, const int64_t* d_a,
                                const int64_t* d_b, int64_t m, int n_hash, uint32_t* d_sig, cudaStream_t st);
-// row-major sig[n][n_hash] -> hash-major sigT[hrows][npitch] plus its negation sigTneg (see mh_kernels.cu)
-int launch_mh_transpose(const uint32_t* d_sig, int64_t n, int n_hash, uint32_t* d_sigT, uint32_t* d_sigTneg,
-                        int64_t npitch, int hrows, cudaStream_t st);
+// row-major sig[n][n_hash] -> hash-major sigT[hrows][npitch], zero padding
+int launch_mh_transpose(const uint32_t* d_sig, int64_t n, int n_hash, uint32_t* d_sigT, int64_t npitch, int hrows,
+                        cudaStream_t st);
 // K3: match counts for rows [row_begin,row_end) into the packed strict-upper-triangle slab
-int launch_mh_match(const uint32_t* d_sigT, const uint32_t* d_sigTneg, int64_t npitch, int hrows, int64_t n,
-                    int64_t row_begin, int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches);
+int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_hash, int64_t n, int64_t row_begin,
+                    int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches);
 // expand a counts slab into the column-major double matrix (both triangles + diagonal of the slab's rows):
 // out = table[count]; the n_hash+1 table entries are computed on the host with the reference's arithmetic
 int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,
