@@ -8,6 +8,7 @@
 //   CharacterVector: (n) ctor, length(), operator[] (read as string, assign string)
 //   NumericMatrix:   (r,c) ctor zero-filled column-major, operator()(i,j), attr("dimnames") = ...
 //   List::create(a, b), as<std::string>(elem)
+//   IntegerVector / NumericVector / IntegerMatrix (only what rpkg/src/dyna_shims.cpp needs, for the shim harness)
 // Nothing here mirrors Rcpp's implementation; it is a behavioural stub.
 #ifndef DYNA_ORACLE_RCPP_STUB_H
 #define DYNA_ORACLE_RCPP_STUB_H
@@ -110,7 +111,32 @@ public:
   std::size_t nrow() const { return nr_; }
   std::size_t ncol() const { return nc_; }
   const double* begin() const { return d_.data(); }
+  double* begin() { return d_.data(); }
   const List& dimnames() const { return dimnames_; }
+};
+
+// --- plain vectors / integer matrix (shim harness only) -------------------------
+template <class T>
+class StubVector {
+  std::vector<T> v_;
+public:
+  StubVector() {}
+  explicit StubVector(std::vector<T> v) : v_(std::move(v)) {}
+  long length() const { return static_cast<long>(v_.size()); }
+  typename std::vector<T>::const_iterator begin() const { return v_.begin(); }
+  typename std::vector<T>::const_iterator end() const { return v_.end(); }
+};
+typedef StubVector<int> IntegerVector;
+typedef StubVector<double> NumericVector;
+
+class IntegerMatrix {
+  int nr_, nc_;
+  std::vector<int> d_;
+public:
+  IntegerMatrix(int r, int c, std::vector<int> d) : nr_(r), nc_(c), d_(std::move(d)) {}
+  int nrow() const { return nr_; }
+  int ncol() const { return nc_; }
+  int operator()(int i, int j) const { return d_[static_cast<std::size_t>(i) + static_cast<std::size_t>(j) * nr_]; }
 };
 
 }  // namespace Rcpp

@@ -1,0 +1,119 @@
+// Rcpp marshalling shims over the C ABI (include/dynaalign_b200.h).  These replace the bodies of the reference's
+// similarityMH (src/minHash.cpp:119) and similarityNW (src/pairwiseSeqAlign.cpp:331): same C++ prototypes, so the
+// generated wrappers in RcppExports.cpp are unchanged.  All R API use (string access, allocation, dimnames)
+// happens here on R's main thread before/after the GPU call; the CUDA side never sees a SEXP.
+#include <Rcpp.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "dynaalign_b200.h"
+
+using namespace Rcpp;
+
+namespace {
+
+struct Flat {
+  std::vector<uint8_t> residues;
+  std::vector<int64_t> offsets;
+};
+
+Flat flatten(const CharacterVector& sequences) {
+  Flat f;
+  const size_t n = sequences.length();
+  f.offsets.assign(n + 1, 0);
+  for (size_t i = 0; i < n; ++i) {
+    const std::string s = as<std::string>(sequences[i]);
+    f.residues.insert(f.residues.end(), s.begin(), s.end());
+    f.offsets[i + 1] = static_cast<int64_t>(f.residues.size());
+  }
+  if (f.residues.empty()) f.residues.push_back(0);
+  return f;
+}
+
+int env_gpus() {
+  const char* e = std::getenv("DYNAALIGN_GPUS");
+  return e ? std::atoi(e) : 1;
+}
+
+void set_dimnames(NumericMatrix& m, size_t n) {
+  CharacterVector labels(n);
+  for (size_t i = 0; i < n; ++i) labels[i] = std::to_string(i + 1);
+  m.attr("dimnames") = List::create(labels, labels);
+}
+
+void raise_on_error(int rc) {
+  if (rc != DYNA_OK) Rcpp::stop("%s", std::string(dyna_last_error()));
+}
+
+}  // namespace
+
+// [[Rcpp::export]]
+NumericMatrix similarityMH(CharacterVector sequences, int k = 4, int n_hash = 50) {
+  const size_t n = sequences.length();
+  const Flat f = flatten(sequences);
+  NumericMatrix similarityMatrix(n, n);
+  // HashFamily seed: std::random_device as in the reference, unless DYNAALIGN_SEED pins it (tests)
+  std::vector<uint32_t> seeds;
+  const uint32_t* seed_ptr = nullptr;
+  if (const char* e = std::getenv("DYNAALIGN_SEED")) {
+    if (n_hash > 0) {
+      seeds.resize(static_cast<size_t>(n_hash));
+      raise_on_error(dyna_hashfamily_seeds(static_cast<uint32_t>(std::strtoul(e, nullptr, 10)), n_hash, seeds.data()));
+      seed_ptr = seeds.data();
+    }
+  }
+  raise_on_error(dyna_similarityMH(f.residues.data(), f.offsets.data(), static_cast<int64_t>(n), k, n_hash, seed_ptr,
+                                   n ? &similarityMatrix(0, 0) : nullptr, env_gpus()));
+  set_dimnames(similarityMatrix, n);
+  return similarityMatrix;
+}
+
+// [[Rcpp::export]]
+NumericMatrix similarityNW(CharacterVector sequences, std::string matrixName = "BLOSUM62", int gapOpen = 10,
+                           int gapExt = 4) {
+  const size_t n = sequences.length();
+  const Flat f = flatten(sequences);
+  NumericMatrix similarityMatrix(n, n);
+  raise_on_error(dyna_similarityNW(f.residues.data(), f.offsets.data(), static_cast<int64_t>(n), matrixName.c_str(),
+                                   gapOpen, gapExt, n ? &similarityMatrix(0, 0) : nullptr, env_gpus()));
+  set_dimnames(similarityMatrix, n);
+  return similarityMatrix;
+}
+
+// GPU half of compute_signature_matrix (R/minHash.R): returns the n_hash x n_docs double matrix, Inf where a
+// document has no shingle.
+// [[Rcpp::export]]
+NumericMatrix mh_signatures_linear(IntegerVector ranks, NumericVector offsets, NumericVector a, NumericVector b,
+                                   double m, int n_hash) {
+  const int64_t n_docs = static_cast<int64_t>(offsets.length()) - 1;
+  std::vector<int32_t> rk(ranks.begin(), ranks.end());
+  if (rk.empty()) rk.push_back(1);
+  std::vector<int64_t> off(offsets.begin(), offsets.end()), av(a.begin(), a.end()), bv(b.begin(), b.end());
+  std::vector<uint32_t> sig(static_cast<size_t>(n_docs) * static_cast<size_t>(n_hash));
+  raise_on_error(dyna_mh_signatures_linear(rk.data(), off.data(), n_docs, av.data(), bv.data(), static_cast<int64_t>(m),
+                                           n_hash, sig.data()));
+  NumericMatrix out(n_hash, n_docs);  // column-major: element (h, doc) at h + doc * n_hash == sig[doc * n_hash + h]
+  for (int64_t d = 0; d < n_docs; ++d)
+    for (int h = 0; h < n_hash; ++h) {
+      const uint32_t v = sig[static_cast<size_t>(d) * n_hash + h];
+      out(h, d) = (v == 0xFFFFFFFFu) ? std::numeric_limits<double>::infinity() : static_cast<double>(v);
+    }
+  return out;
+}
+
+// GPU half of compute_distance_matrix: codes is the n_hash x n_docs integer matrix of per-row relabelled signatures
+// [[Rcpp::export]]
+NumericMatrix mh_distance_matrix(IntegerMatrix codes) {
+  const int n_hash = codes.nrow();
+  const int64_t n_docs = codes.ncol();
+  std::vector<uint32_t> sig(static_cast<size_t>(n_docs) * static_cast<size_t>(n_hash));
+  for (int64_t d = 0; d < n_docs; ++d)
+    for (int h = 0; h < n_hash; ++h) sig[static_cast<size_t>(d) * n_hash + h] = static_cast<uint32_t>(codes(h, d));
+  NumericMatrix out(n_docs, n_docs);
+  raise_on_error(dyna_mh_match_matrix(sig.data(), n_docs, n_hash, DYNA_MH_DISTANCE, n_docs ? &out(0, 0) : nullptr, 1));
+  return out;
+}
