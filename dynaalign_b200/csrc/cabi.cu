@@ -234,7 +234,7 @@ extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
 // NW plan
 // =====================================================================================================
 struct NwClass {
-  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp kernel multipass
+  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp kernel multipass, 4 two-pairs-per-warp 16-bit kernel
   int R;
   std::vector<NwUnit> units;
   DevBuf<NwUnit> d_units;
@@ -306,6 +306,15 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   }
   p->slant = (smin + 2 * (int64_t)gap_ext >= -128) && (smax + 2 * (int64_t)gap_ext <= 127);
   if (const char* e = getenv("DYNA_NW_SLANT")) p->slant = p->slant && (atoi(e) != 0);
+  // 16-bit two-pairs-per-warp kernel: every slanted DP value of a (row, column) pair lies in
+  //   [smin - 3*go + 2*ge,  max(smax,0)*min(m,n) + (m+n)*ge]   (DESIGN.md section 4), which must fit int16 with room
+  // for the flat -30000 sentinel below and the "- go" of a gap opening above.
+  bool pack16 = p->slant && gap_ext >= 0 && gap_open >= 0 && (smin - 3ll * gap_open + 2ll * gap_ext) >= -24000;
+  if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
+  auto fits16 = [&](int m) {
+    const int64_t hi = (int64_t)std::max(smax, 0) * std::min<int64_t>(m, max_len) + ((int64_t)m + max_len) * gap_ext + gap_open;
+    return pack16 && m > kNwThreadMaxRows && m <= 32 * kNwWarp2MaxR && hi <= 32000;
+  };
 
   // encode residues, 32-bit offsets
   std::vector<uint8_t> codes((size_t)total + 4);
@@ -342,6 +351,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     int kind, R, step;
     if (m == 0) { kind = 0; R = 0; step = 4096; }
     else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
+    else if (fits16(m)) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
     else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
     else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
     NwClass* c = get_class(kind, R);
@@ -392,6 +402,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       case 0: DYNA_TRY(launch_nw_empty_rows(d, c->d_units.p, nu, st)); break;
       case 1: DYNA_TRY(launch_nw_thread(c->R, p->slant, d, c->d_units.p, nu, st)); break;
       case 2: DYNA_TRY(launch_nw_warp(c->R, p->slant, false, d, c->d_units.p, nu, nullptr, 0, st)); break;
+      case 4: DYNA_TRY(launch_nw_warp2(c->R, d, c->d_units.p, nu, st)); break;
       default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, st)); break;
     }
     ++p->launches;

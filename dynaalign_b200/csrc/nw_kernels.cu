@@ -272,6 +272,188 @@ nw_warp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5x2: one warp per TWO pairs, 16-bit lanes (s16x2 DPX)
+//
+// The 32-bit kernel is bound by the ALU pipe (8 of its 10 instructions per cell issue there at 16 lanes/clk per
+// sub-partition).  When every DP value provably fits 16 bits (host check: slanted values live in
+// [smin - 3go + 2ge, smax*min(m,n) + (m+n)*ge], see cabi.cu), two column sequences share a warp: the low half of
+// every score register belongs to pair A = (row, jA), the high half to pair B = (row, jB), and VIADDMNMX.S16x2 /
+// VIMNMX.S16x2 (which returns both ">=" predicates) update two cells per instruction:
+//     sP   = PRMT(wA, wB)                 packed sign-extended scores                     ALU
+//     Mraw = VIADDMNMX.S16x2(diag, sP, MIN)                                               ALU
+//     g    = VIMNMX.S16x2(F, E)  -> pU_A, pU_B                                            ALU
+//     H    = VIMNMX.S16x2(Mraw, g) -> pD_A, pD_B                                          ALU
+//     E'   = VIADDMNMX.S16x2(H, -go, E);  F' = VIADDMNMX.S16x2(H, -go, F)                 ALU x2
+//     per pair: inc = PRMT, S = SEL(pU), @pD S = diagS + inc                              ALU x2, other x1
+// = 10 ALU-pipe instructions per two cells instead of 16.  The traceback statistics stay 32-bit per pair.
+// The shorter of the two column sequences is padded with residue class 24 (zero profile) and its result is
+// captured when its last real column has been processed; the values computed past its end are never used.
+// "Minus infinity" is a flat sentinel (-30000) in the slanted domain: it only has to lose every comparison once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSentinel16 = -30000;
+
+__device__ __forceinline__ uint32_t pack16(int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); }
+
+template <int R>
+__device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
+                                              const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
+                                              uint32_t (&SBn)[R], const uint32_t (&pwA)[Strip<R>::RW],
+                                              const uint32_t (&pwB)[Strip<R>::RW], uint32_t diagH, uint32_t dSA,
+                                              uint32_t dSB, uint32_t F, uint32_t upSA, uint32_t upSB, uint32_t ngo2,
+                                              uint32_t one, uint32_t& outF) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t wA = pwA[k >> 1], wB = pwB[k >> 1];
+    const uint32_t sP = (k & 1) ? prmt<0xE6A2>(wA, wB) : prmt<0xC480>(wA, wB);  // [sext16(sA) | sext16(sB) << 16]
+    const uint32_t incA = (k & 1) ? prmt<0x5354>(wA, one) : prmt<0x5154>(wA, one);
+    const uint32_t incB = (k & 1) ? prmt<0x5354>(wB, one) : prmt<0x5154>(wB, one);
+    const uint32_t E = El[k];
+    const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    bool puB, puA, pdB, pdA;
+    const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);   // pred_hi -> pair B, pred_lo -> pair A
+    const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    uint32_t SA = puA ? upSA : SAo[k];
+    if (pdA) SA = dSA + incA;
+    uint32_t SB = puB ? upSB : SBo[k];
+    if (pdB) SB = dSB + incB;
+    diagH = Ho[k];
+    dSA = SAo[k];
+    dSB = SBo[k];
+    Hn[k] = H;
+    SAn[k] = SA;
+    SBn[k] = SB;
+    El[k] = __viaddmax_s16x2(H, ngo2, E);
+    F = __viaddmax_s16x2(H, ngo2, F);
+    upSA = SA;
+    upSB = SB;
+  }
+  outF = F;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kWarpThreads)
+nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  using S = Strip<R>;
+  __shared__ uint32_t prof[25 * 32 * S::RWS];  // class 24 = padding residue, all-zero entries
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = kWarpThreads / 32;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  const uint32_t sent2 = pack16(kSentinel16);
+  const uint32_t bord2 = pack16(ge - go);  // slanted border: Bd(k) + k*ge = -go + ge for every k >= 1
+  const uint32_t one = d.one;
+  const unsigned full = 0xFFFFFFFFu;
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row;
+    const int m = d.off[row + 1] - d.off[row];
+    __syncthreads();
+    build_profile<R, 32>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, kWarpThreads);
+    for (int idx = tid; idx < 32 * S::RWS; idx += kWarpThreads) prof[24 * 32 * S::RWS + idx] = 0u;
+    __syncthreads();
+    const int lm = (m - 1) / R;
+    const int km = (m - 1) - lm * R;
+    const int r0 = lane * R;
+    const int npairs2 = (un.j_count + 1) >> 1;
+
+    for (int pp = warp; pp < npairs2; pp += nwarps) {
+      int jA = un.j_begin + 2 * pp;
+      int jB = jA + 1;
+      const bool hasB = (jB < un.j_begin + un.j_count);
+      if (!hasB) jB = jA;
+      int nA = d.off[jA + 1] - d.off[jA], nB = d.off[jB + 1] - d.off[jB];
+      if (nB > nA) {  // A is the longer column sequence
+        int tj = jA; jA = jB; jB = tj;
+        int tn = nA; nA = nB; nB = tn;
+      }
+      const uint8_t* __restrict__ bA = d.codes + d.off[jA];
+      const uint8_t* __restrict__ bB = d.codes + d.off[jB];
+
+      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        H0[k] = H1[k] = bord2;
+        El[k] = sent2;
+        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+      }
+      uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
+      uint32_t prevUpSA = 0u, prevUpSB = 0u;
+      uint32_t outH = 0u, outF = 0u, outSA = 0u, outSB = 0u;
+      uint32_t resB = 0u;
+      const int T = nA + lm;
+      for (int t0 = 0; t0 < T; t0 += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const int t = t0 + ph;
+          const int jc = t - lane;
+          uint32_t rH = __shfl_up_sync(full, outH, 1);
+          uint32_t rF = __shfl_up_sync(full, outF, 1);
+          uint32_t rSA = __shfl_up_sync(full, outSA, 1);
+          uint32_t rSB = __shfl_up_sync(full, outSB, 1);
+          if (lane == 0) {
+            rH = bord2;
+            rF = sent2;
+            rSA = 0u;
+            rSB = 0u;
+          }
+          if (jc >= 0 && jc < nA && lane <= lm) {
+            const int cA = bA[jc];
+            const int cB = (jc < nB) ? (int)bB[jc] : 24;
+            uint32_t pwA[S::RW], pwB[S::RW];
+            const uint32_t* pa = prof + cA * (32 * S::RWS) + lane * S::RWS;
+            const uint32_t* pb = prof + cB * (32 * S::RWS) + lane * S::RWS;
+#pragma unroll
+            for (int w = 0; w < S::RW; ++w) {
+              pwA[w] = pa[w];
+              pwB[w] = pb[w];
+            }
+            if (ph == 0) {
+              strip_column2<R>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2,
+                               one, outF);
+              outH = H1[R - 1];
+              outSA = SA1[R - 1];
+              outSB = SB1[R - 1];
+            } else {
+              strip_column2<R>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2,
+                               one, outF);
+              outH = H0[R - 1];
+              outSA = SA0[R - 1];
+              outSB = SB0[R - 1];
+            }
+            prevUpH = rH;
+            prevUpSA = rSA;
+            prevUpSB = rSB;
+            if (lane == lm && jc == nB - 1) {  // the shorter sequence ends here: capture its result
+#pragma unroll
+              for (int k = 0; k < R; ++k)
+                if (k == km) resB = (ph == 0) ? SB1[k] : SB0[k];
+            }
+          }
+        }
+      }
+      const bool in1 = (((lm + nA) & 1) != 0);
+      uint32_t resA = 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (k == km) resA = in1 ? SA1[k] : SA0[k];
+      resA = __shfl_sync(full, resA, lm);
+      resB = __shfl_sync(full, resB, lm);
+      if (lane == 0) {
+        const int64_t slotA = pair_slot(d.n, row, jA, d.slab_base);
+        d.matches[slotA] = resA >> 16;
+        d.length[slotA] = (uint32_t)(m + nA) - (resA & 0xFFFFu);
+        if (hasB) {
+          const int64_t slotB = pair_slot(d.n, row, jB, d.slab_base);
+          d.matches[slotB] = resB >> 16;
+          d.length[slotB] = (uint32_t)(m + nB) - (resB & 0xFFFFu);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: one thread per pair (rows <= R <= 32)
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreadThreads = 128;
@@ -373,6 +555,13 @@ int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int 
   return DYNA_OK;
 }
 
+template <int R>
+int launch_warp2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  nw_warp2_kernel<R><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
 int launch_warp_multipass(bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, int32_t* d_scratch,
                           int max_cols, cudaStream_t st) {
   const int grid = std::min(num_units, kNwMultiPassGrid);
@@ -427,6 +616,21 @@ int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, con
 #undef DYNA_CASE
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw warp kernel: unsupported strip height %d", R);
+  }
+}
+
+int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_warp2_R<RR>(d, d_units, num_units, st);
+    DYNA_CASE(2) DYNA_CASE(3) DYNA_CASE(4) DYNA_CASE(5) DYNA_CASE(6) DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9)
+    DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12) DYNA_CASE(13) DYNA_CASE(14) DYNA_CASE(15) DYNA_CASE(16) DYNA_CASE(17)
+    DYNA_CASE(18) DYNA_CASE(19) DYNA_CASE(20)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw warp2 kernel: unsupported strip height %d", R);
   }
 }
 

@@ -26,6 +26,7 @@ struct NwDeviceData {
 
 constexpr int kNwThreadMaxRows = 32;  // rows handled by the thread-per-pair kernel
 constexpr int kNwWarpMaxR = 24;       // rows per lane of the warp-per-pair kernel (32*24 = 768 rows per pass)
+constexpr int kNwWarp2MaxR = 20;      // strip height limit of the two-pairs-per-warp 16-bit kernel (register budget)
 constexpr int kNwWarpUnitPairs = 32;  // pairs per unit (8 warps x 4)
 constexpr int kNwThreadUnitPairs = 512;
 constexpr int kNwMultiPassGrid = 148 * 2;
@@ -41,6 +42,8 @@ int launch_nw_thread(int R, bool slant, const NwDeviceData& d, const NwUnit* d_u
 // scratch: only for multipass (rows longer than 32*R): kNwMultiPassGrid * 8 warps * 3 * max_cols ints
 int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, const NwUnit* d_units, int num_units, int32_t* d_scratch,
                    int max_cols, cudaStream_t st);
+// two pairs per warp in 16-bit lanes (host guarantees the value range); R in 2..kNwWarp2MaxR
+int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 // (matches, length) slab -> column-major doubles, both triangles (reference: src/pairwiseSeqAlign.cpp:311,349-350)
 int launch_nw_expand(const uint32_t* d_matches, const uint32_t* d_length, int64_t n, int64_t row_begin, int64_t row_end,
                      double* d_out, cudaStream_t st);

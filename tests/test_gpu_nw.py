@@ -143,3 +143,24 @@ def test_h3n2_config2_full(golden, h3n2):
     assert (m == m.T).all() and (np.diag(m) == 1.0).all()
     for s in golden["nw_h3n2_1000_sample"]:
         assert m[s["i"], s["j"]] == s["sim"]
+
+
+def test_packed16_and_32bit_kernels_agree(monkeypatch):
+    # rows of 33..640 residues take the two-pairs-per-warp 16-bit kernel by default; DYNA_NW_PACK16=0 forces the 32-bit one
+    rng = np.random.default_rng(16)
+    seqs = random_seqs(rng, 25, 33, 640, "ARNDCQEGHILKMFPSTWYV") + random_seqs(rng, 6, 0, 40) + ["A" * 500, "W" * 640, "C" * 333]
+    rng.shuffle(seqs)
+    for name, go, ge in [("BLOSUM62", 10, 4), ("BLOSUM100", 0, 0), ("BLOSUM45", 12, 1), ("BLOSUM80", 2, 7)]:
+        a = da.nw_pair_stats(seqs, name, go, ge)
+        monkeypatch.setenv("DYNA_NW_PACK16", "0")
+        b = da.nw_pair_stats(seqs, name, go, ge)
+        monkeypatch.delenv("DYNA_NW_PACK16")
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    check_stats(seqs[:14], "BLOSUM62", 10, 4)
+
+
+def test_packed16_range_guard():
+    # long, self-similar sequences with a high-scoring table push the slanted score past int16: must fall back, stay exact
+    seqs = ["W" * 640, "W" * 600, "W" * 64 + "A" * 500, "C" * 640]
+    check_stats(seqs, "BLOSUM100", 1, 30)
+    check_stats(seqs, "BLOSUM62", 10, 4)
