@@ -123,8 +123,69 @@ struct dyna_mh_plan {
   DevBuf<int64_t> off;
   DevBuf<uint32_t> seeds, sig, sigT;
   DevBuf<uint16_t> counts;
+  // 16-bit relabelled copy for the HSET2 match path (large inputs only)
+  bool use16 = false;
+  DevBuf<uint32_t> keys_out, vals_in, vals_out, sigP;
+  DevBuf<int> seg_begin, seg_end, overflow;
+  DevBuf<uint8_t> cub_temp;
+  MhRelabelWork work;
   bool have_sequences = false, have_sig = false, have_sigT = false;
 };
+
+namespace {
+// threshold below which the relabelling overhead is not worth it
+constexpr int64_t kMhPack16MinN = 2048;
+
+int mh_plan_setup16(dyna_mh_plan* p) {
+  const int64_t items = p->npitch * (int64_t)p->hrows;
+  bool want = p->n >= kMhPack16MinN && items < (1ll << 31) && p->row_end > p->row_begin;
+  if (const char* e = getenv("DYNA_MH_PACK16")) want = (atoi(e) != 0) && items < (1ll << 31) && p->row_end > p->row_begin;
+  p->use16 = want;
+  if (!want) return DYNA_OK;
+  const int hrows2 = mh_hrows2(p->n_hash);
+  DYNA_TRY(p->keys_out.alloc((size_t)items));
+  DYNA_TRY(p->vals_in.alloc((size_t)items));
+  DYNA_TRY(p->vals_out.alloc((size_t)items));
+  DYNA_TRY(p->sigP.alloc((size_t)hrows2 * p->npitch));
+  DYNA_TRY(p->seg_begin.alloc((size_t)p->hrows));
+  DYNA_TRY(p->seg_end.alloc((size_t)p->hrows));
+  DYNA_TRY(p->overflow.alloc(1));
+  const size_t tb = mh_relabel_temp_bytes(p->npitch, p->hrows);
+  DYNA_TRY(p->cub_temp.alloc(tb + 16));
+  std::vector<int> b((size_t)p->hrows), e((size_t)p->hrows);
+  for (int h = 0; h < p->hrows; ++h) {
+    b[(size_t)h] = (int)(h * p->npitch);
+    e[(size_t)h] = (int)(h * p->npitch + p->n);
+  }
+  DYNA_CUDA(cudaMemcpy(p->seg_begin.p, b.data(), sizeof(int) * b.size(), cudaMemcpyHostToDevice));
+  DYNA_CUDA(cudaMemcpy(p->seg_end.p, e.data(), sizeof(int) * e.size(), cudaMemcpyHostToDevice));
+  DYNA_TRY(launch_mh_iota(p->vals_in.p, p->npitch, p->hrows, nullptr));
+  DYNA_CUDA(cudaDeviceSynchronize());
+  p->work.temp = p->cub_temp.p;
+  p->work.temp_bytes = tb;
+  p->work.keys_out = p->keys_out.p;
+  p->work.vals_in = p->vals_in.p;
+  p->work.vals_out = p->vals_out.p;
+  p->work.seg_begin = p->seg_begin.p;
+  p->work.seg_end = p->seg_end.p;
+  p->work.sigP = p->sigP.p;
+  p->work.overflow = p->overflow.p;
+  return DYNA_OK;
+}
+
+// transpose (+ relabel when the 16-bit path is on): everything the match kernel needs, from sig[n][n_hash]
+int mh_plan_prepare_match_inputs(dyna_mh_plan* p, cudaStream_t st, int* launches) {
+  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->npitch, p->hrows, st));
+  int l = 1;
+  if (p->use16) {
+    int lr = 0;
+    DYNA_TRY(launch_mh_relabel(p->sigT.p, p->n, p->n_hash, p->npitch, p->hrows, p->work, st, &lr));
+    l += lr;
+  }
+  if (launches) *launches = l;
+  return DYNA_OK;
+}
+}  // namespace
 
 extern "C" dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_begin, int64_t row_end, int device) {
   if (n <= 0 || n_hash <= 0 || n_hash > 65535 || row_begin < 0 || row_end > n || row_begin > row_end) {
@@ -143,6 +204,7 @@ extern "C" dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_
   p->pairs = tri_strict_rows(n, row_end) - tri_strict_rows(n, row_begin);
   if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch) || p->counts.alloc((size_t)p->pairs))
     return nullptr;
+  if (mh_plan_setup16(p.get()) != DYNA_OK) return nullptr;
   return p.release();
 }
 
@@ -173,9 +235,10 @@ extern "C" int dyna_mh_plan_upload_signatures(dyna_mh_plan* p, const uint32_t* s
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DYNA_CUDA(cudaMemcpyAsync(p->sig.p, sig, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyHostToDevice, st));
-  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->npitch, p->hrows, st));
+  int l = 0;
+  DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l));
   p->have_sig = p->have_sigT = true;
-  p->launches = 1;
+  p->launches = l;
   return DYNA_OK;
 }
 
@@ -185,9 +248,10 @@ extern "C" int dyna_mh_plan_run_signatures(dyna_mh_plan* p, void* stream) {
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
-  DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->npitch, p->hrows, st));
+  int l = 0;
+  DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l));
   p->have_sig = p->have_sigT = true;
-  p->launches = 2;
+  p->launches = 1 + l;
   return DYNA_OK;
 }
 
@@ -197,7 +261,8 @@ extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int l = 0;
-  DYNA_TRY(launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, p->row_begin, p->row_end, p->counts.p, st, &l));
+  DYNA_TRY(launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, p->row_begin, p->row_end, p->counts.p,
+                           p->use16 ? p->sigP.p : nullptr, p->use16 ? p->overflow.p : nullptr, st, &l));
   p->launches = l;
   return DYNA_OK;
 }
@@ -313,7 +378,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
   auto fits16 = [&](int m) {
     const int64_t hi = (int64_t)std::max(smax, 0) * std::min<int64_t>(m, max_len) + ((int64_t)m + max_len) * gap_ext + gap_open;
-    return pack16 && m > kNwThreadMaxRows && m <= 32 * kNwWarp2MaxR && hi <= 32000;
+    return pack16 && m > kNwThreadMaxRows && m <= 32 * kNwWarp2MaxR && hi <= 32000 && (int64_t)m + max_len <= 65535;
   };
 
   // encode residues, 32-bit offsets

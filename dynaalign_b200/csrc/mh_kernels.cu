@@ -15,6 +15,9 @@
 #include "mh_kernels.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdlib>
@@ -277,6 +280,35 @@ __device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty
   }
 }
 
+// 16-bit path: every hash row has been relabelled to dense codes that are valid, distinct fp16 NORMAL numbers
+// (mh_relabel below), two consecutive hash components of a sequence share one 32-bit word, and one HSET2.EQ
+// compares both halves at once (ALU pipe, 2 compares per lane-op).  The 0xFFFF-per-equal-half mask is subtracted
+// from a 32-bit accumulator with a 2-input add (other integer pipe): after N steps the low half holds the number of
+// low-half matches L and the high half (Hc - L) mod 2^16, so matches = low + ((high + low) & 0xFFFF).
+// The subtraction is issued as IMAD (acc = m * (-1) + acc, multiplier in a register so it is not strength-reduced):
+// plain subs get fused pairwise into 3-input IADD3, which issues on the ALU pipe next to HSET2 and costs 50 %.
+__device__ __forceinline__ void count_eq2(uint32_t& acc, uint32_t a, uint32_t b, uint32_t minus1) {
+  const uint32_t m = __heq2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(m), "r"(minus1));
+}
+
+__device__ __forceinline__ void match_stage_compute16(const MatchStage& st, int ty, int tx, uint32_t (&acc)[8][8],
+                                                      uint32_t minus1) {
+#pragma unroll
+  for (int hh = 0; hh < kMatchBK; ++hh) {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh][ty * 4]);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh][64 + ty * 4]);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh][tx * 4]);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(&st.b[hh][64 + tx * 4]);
+    const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) count_eq2(acc[i][j], av[i], bv[j], minus1);
+  }
+}
+
 // counts tile -> packed strict upper triangle, staged through shared memory for coalesced rows
 __device__ __forceinline__ void match_store_tile(uint16_t (*cs)[kCsPitch], const uint32_t (&ne)[8][8], int pad, int ty,
                                                  int tx, int lx, int lw, int64_t r0, int64_t c0, int64_t n,
@@ -344,9 +376,17 @@ struct TmapPair {
   alignas(64) unsigned char a[128];  // CUtensorMap over sigT (rows and columns of a tile read the same tensor)
 };
 
+// PAIRS16 = false: u32 signatures, ISETP path.  PAIRS16 = true: relabelled 16-bit codes, two hash components per word.
+// `rows` = rows of the tensor the boxes walk, `pad` = matches contributed by padding (subtracted before the store).
+// `gate`: optional device flag; the kernel is a no-op unless *gate == gate_value (lets the host enqueue both paths
+// without a synchronising read-back of the relabelling outcome).
+template <bool PAIRS16>
 __global__ void __launch_bounds__(kMatchThreads, 2)
-mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int n_hash, int64_t n, int64_t tile_base, int64_t row_begin,
-                    int64_t row_end, uint16_t* __restrict__ counts, int64_t slab_base, int64_t T0, int64_t num_tiles) {
+mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int rows, int pad, int64_t n, int64_t tile_base, int64_t row_begin,
+                    int64_t row_end, uint16_t* __restrict__ counts, int64_t slab_base, int64_t T0, int64_t num_tiles,
+                    const int* __restrict__ gate, int gate_value) {
+  if (gate != nullptr && *gate != gate_value) return;
+  const uint32_t minus1 = (uint32_t)(gate_value >> 8) - 1u;  // opaque 0xFFFFFFFF (gate_value is 0 or 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MatchStage* stages = reinterpret_cast<MatchStage*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kMatchStages * sizeof(MatchStage));
@@ -355,7 +395,7 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int n_hash, 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int lx = tid & 31, lw = tid >> 5;
-  const int nkb = hrows / kMatchBK;
+  const int nkb = rows / kMatchBK;
 
   if (tid == 0) {
     for (int s = 0; s < kMatchStages; ++s) mbar_init(&full[s], 1);
@@ -390,10 +430,17 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int hrows, int n_hash, 
       const uint32_t slot = it % kMatchStages;
       if (tid == 0 && kb + kMatchStages - 1 < nkb) issue(kb + kMatchStages - 1, (it + kMatchStages - 1) % kMatchStages);
       mbar_wait(&full[slot], (it / kMatchStages) & 1u);
-      match_stage_compute(stages[slot], ty, tx, ne);
+      if (PAIRS16) match_stage_compute16(stages[slot], ty, tx, ne, minus1);
+      else match_stage_compute(stages[slot], ty, tx, ne);
       __syncthreads();  // slot free for the load issued at the top of the next iteration
     }
-    match_store_tile(cs, ne, hrows - n_hash, ty, tx, lx, lw, r0, c0, n, row_begin, row_end, slab_base, counts);
+    if (PAIRS16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ne[i][j] = (ne[i][j] & 0xFFFFu) + ((ne[i][j] + (ne[i][j] >> 16)) & 0xFFFFu);
+    }
+    match_store_tile(cs, ne, pad, ty, tx, lx, lw, r0, c0, n, row_begin, row_end, slab_base, counts);
     __syncthreads();  // cs (aliasing the ring) fully read before the next tile's loads land
   }
 }
@@ -452,6 +499,70 @@ mh_match_ldg_kernel(const uint32_t* __restrict__ sigT, int64_t npitch, int hrows
     __syncthreads();
     match_store_tile(cs, ne, hrows - n_hash, ty, tx, lx, lw, r0, c0, n, row_begin, row_end, slab_base, counts);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// relabelling for the 16-bit match path.  Only equality matters to the match count, so each hash row may be
+// replaced by ANY injective code of its values.  Rows are sorted (CUB segmented radix sort of (value, sequence
+// index) pairs -- a library helper, not the hot op), dense ranks are assigned by a block-wide flag scan, and rank r
+// becomes the r-th fp16 bit pattern that is a NORMAL number (no NaN, no +-0, no denormal: 0x0400..0x7BFF, then
+// 0x8400..0xFBFF -> 61,440 codes), so that HSET2.EQ compares them exactly like integers.  A row with more distinct
+// values than codes raises `overflow`, which gates the kernels back to the 32-bit path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCodesPerSign = 0x7C00 - 0x0400;  // 30,720
+constexpr int kMaxCodes = 2 * kCodesPerSign;    // 61,440
+
+__global__ void mh_iota_kernel(uint32_t* __restrict__ vals, int64_t npitch, int rows) {
+  const int64_t total = npitch * rows;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x)
+    vals[q] = (uint32_t)(q % npitch);
+}
+
+__global__ void __launch_bounds__(1024)
+mh_rank_scatter_kernel(const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ idx_sorted, int64_t n,
+                       int64_t npitch, uint16_t* __restrict__ sigP16, int* __restrict__ overflow, uint32_t max_codes) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t chunk_tot;
+  const int h = blockIdx.x;
+  const uint32_t* keys = keys_sorted + (int64_t)h * npitch;
+  const uint32_t* idx = idx_sorted + (int64_t)h * npitch;
+  uint16_t* out = sigP16 + 2 * ((int64_t)(h >> 1) * npitch) + (h & 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t running = 0;  // distinct values seen before this chunk
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t p = base + threadIdx.x;
+    const bool valid = p < n;
+    const uint32_t key = valid ? keys[p] : 0u;
+    uint32_t flag = (valid && (p == 0 || key != keys[p - 1])) ? 1u : 0u;
+    uint32_t incl = flag;  // inclusive scan of the "new value" flags
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_tot[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, d);
+        if (lane >= d) w += v;
+      }
+      warp_tot[lane] = w;  // inclusive totals per warp
+      if (lane == 31) chunk_tot = w;
+    }
+    __syncthreads();
+    const uint32_t rank = running + (warp ? warp_tot[warp - 1] : 0u) + incl - 1u;
+    if (valid) {
+      const uint32_t r = rank < max_codes ? rank : 0u;
+      const uint32_t code = r < (uint32_t)kCodesPerSign ? 0x0400u + r : 0x8400u + (r - kCodesPerSign);
+      out[2 * (int64_t)idx[p]] = (uint16_t)code;
+    }
+    running += chunk_tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && running > max_codes) atomicExch(overflow, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,38 +655,101 @@ static int encode_sig_tmap(void* out128, const uint32_t* base, int64_t npitch, i
   return DYNA_OK;
 }
 
-int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_hash, int64_t n, int64_t row_begin,
-                    int64_t row_end, uint16_t* d_counts, cudaStream_t st, int* launches) {
-  if (launches) *launches = 0;
-  if (row_end <= row_begin || n < 2) return DYNA_OK;
+size_t mh_relabel_temp_bytes(int64_t npitch, int hrows) {
+  size_t bytes = 0;
+  cub::DeviceSegmentedRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                           (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(npitch * hrows), hrows,
+                                           (const int*)nullptr, (const int*)nullptr, 0, 32, (cudaStream_t)0);
+  return bytes;
+}
+
+int launch_mh_iota(uint32_t* d_vals, int64_t npitch, int rows, cudaStream_t st) {
+  mh_iota_kernel<<<kNumSMsB200 * 8, 256, 0, st>>>(d_vals, npitch, rows);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_relabel(const uint32_t* d_sigT, int64_t n, int n_hash, int64_t npitch, int hrows, const MhRelabelWork& w,
+                      cudaStream_t st, int* launches) {
+  // sort every hash row (value, sequence index); rows h >= n_hash are padding and are not touched
+  size_t bytes = w.temp_bytes;
+  cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairs(w.temp, bytes, d_sigT, w.keys_out, w.vals_in, w.vals_out,
+                                                           (int)(npitch * hrows), n_hash, w.seg_begin, w.seg_end, 0, 32, st);
+  if (e != cudaSuccess) return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: segmented sort failed: %s", cudaGetErrorString(e));
+  DYNA_CUDA(cudaMemsetAsync(w.sigP, 0, sizeof(uint32_t) * (size_t)npitch * (size_t)mh_hrows2(n_hash), st));
+  DYNA_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+  uint32_t max_codes = (uint32_t)kMaxCodes;
+  if (const char* e = getenv("DYNA_MH_MAXCODES")) max_codes = std::min<uint32_t>(max_codes, (uint32_t)atoi(e));  // tests: force the fallback
+  mh_rank_scatter_kernel<<<n_hash, 1024, 0, st>>>(w.keys_out, w.vals_out, n, npitch, reinterpret_cast<uint16_t*>(w.sigP),
+                                                  w.overflow, max_codes);
+  DYNA_CUDA(cudaGetLastError());
+  if (launches) *launches = 1;
+  return DYNA_OK;
+}
+
+static int match_geometry(int64_t n, int64_t row_begin, int64_t row_end, int64_t& tile_base, int64_t& T0, int64_t& num_tiles,
+                          int& grid) {
   // tiles are aligned to 128 sequences globally (TMA box origins must be 16-byte aligned); rows of the first tile
   // row that precede row_begin are computed but not stored
-  const int64_t tile_base = (row_begin / kMatchBM) * kMatchBM;
-  const int64_t T0 = (n - tile_base + kMatchBM - 1) / kMatchBM;
+  tile_base = (row_begin / kMatchBM) * kMatchBM;
+  T0 = (n - tile_base + kMatchBM - 1) / kMatchBM;
   const int64_t NA = (row_end - tile_base + kMatchBM - 1) / kMatchBM;
-  const int64_t num_tiles = NA * T0 - NA * (NA - 1) / 2;
+  num_tiles = NA * T0 - NA * (NA - 1) / 2;
+  grid = (int)std::min<int64_t>(num_tiles, (int64_t)kNumSMsB200 * 2);
+  return DYNA_OK;
+}
+
+static int ensure_tma_smem() {
+  const size_t smem = kMatchStages * sizeof(MatchStage) + kMatchStages * sizeof(uint64_t);
+  static_assert(kMatchStages * sizeof(MatchStage) >= sizeof(uint16_t) * kMatchBM * kCsPitch, "staging tile must fit the ring");
+  static bool attr_done = false;
+  if (!attr_done) {
+    DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  return DYNA_OK;
+}
+
+int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_hash, int64_t n, int64_t row_begin,
+                    int64_t row_end, uint16_t* d_counts, const uint32_t* d_sigP, const int* d_overflow, cudaStream_t st,
+                    int* launches) {
+  if (launches) *launches = 0;
+  if (row_end <= row_begin || n < 2) return DYNA_OK;
+  int64_t tile_base, T0, num_tiles;
+  int grid;
+  match_geometry(n, row_begin, row_end, tile_base, T0, num_tiles, grid);
   const int64_t slab_base = tri_strict_rows(n, row_begin);
-  const int grid = (int)std::min<int64_t>(num_tiles, (int64_t)kNumSMsB200 * 2);
   const char* mode = getenv("DYNA_MH_MATCH");
   if (mode && strcmp(mode, "ldg") == 0) {
     mh_match_ldg_kernel<<<grid, kMatchThreads, 0, st>>>(d_sigT, npitch, hrows, n_hash, n, tile_base, row_begin, row_end,
                                                         d_counts, slab_base, T0, num_tiles);
-  } else {
-    if (npitch >= (1ll << 31)) return fail(DYNA_ERR_UNSUPPORTED, "too many sequences for the TMA match kernel");
-    TmapPair tm;
-    DYNA_TRY(encode_sig_tmap(tm.a, d_sigT, npitch, hrows));
-    const size_t smem = kMatchStages * sizeof(MatchStage) + kMatchStages * sizeof(uint64_t);
-    static_assert(kMatchStages * sizeof(MatchStage) >= sizeof(uint16_t) * kMatchBM * kCsPitch, "staging tile must fit the ring");
-    static bool attr_done = false;
-    if (!attr_done) {
-      DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_done = true;
-    }
-    mh_match_tma_kernel<<<grid, kMatchThreads, smem, st>>>(tm, hrows, n_hash, n, tile_base, row_begin, row_end, d_counts, slab_base, T0,
-                                                           num_tiles);
+    DYNA_CUDA(cudaGetLastError());
+    if (launches) *launches = 1;
+    return DYNA_OK;
   }
+  if (npitch >= (1ll << 31)) return fail(DYNA_ERR_UNSUPPORTED, "too many sequences for the TMA match kernel");
+  DYNA_TRY(ensure_tma_smem());
+  const size_t smem = kMatchStages * sizeof(MatchStage) + kMatchStages * sizeof(uint64_t);
+  TmapPair tm;
+  int nl = 0;
+  if (d_sigP) {
+    // 16-bit codes, two hash components per word; runs only if the relabelling did not overflow
+    const int rows2 = mh_hrows2(n_hash);
+    DYNA_TRY(encode_sig_tmap(tm.a, d_sigP, npitch, rows2));
+    mh_match_tma_kernel<true><<<grid, kMatchThreads, smem, st>>>(tm, rows2, 2 * rows2 - n_hash, n, tile_base, row_begin,
+                                                                 row_end, d_counts, slab_base, T0, num_tiles, d_overflow, 0);
+    DYNA_CUDA(cudaGetLastError());
+    ++nl;
+  }
+  // 32-bit signatures: always when there is no 16-bit copy, otherwise only if the relabelling overflowed
+  DYNA_TRY(encode_sig_tmap(tm.a, d_sigT, npitch, hrows));
+  mh_match_tma_kernel<false><<<grid, kMatchThreads, smem, st>>>(tm, hrows, hrows - n_hash, n, tile_base, row_begin, row_end,
+                                                                d_counts, slab_base, T0, num_tiles,
+                                                                d_sigP ? d_overflow : nullptr, 1);
   DYNA_CUDA(cudaGetLastError());
-  if (launches) *launches = 1;
+  ++nl;
+  if (launches) *launches = nl;
   return DYNA_OK;
 }
 

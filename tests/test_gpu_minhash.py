@@ -130,3 +130,43 @@ def test_linear_signatures_large_values():
                                                         _lib.ptr(a, C.c_int64), _lib.ptr(b, C.c_int64), m, 30,
                                                         _lib.ptr(got, C.c_uint32)))
         assert (got == want).all()
+
+
+@pytest.mark.parametrize("n,n_hash", [(2, 1), (130, 7), (300, 50), (700, 501), (2500, 100)])
+def test_match_counts_16bit_relabelled_path(n, n_hash, monkeypatch):
+    # HSET2 path: rows relabelled to fp16-safe dense codes, two hash components per word (odd n_hash -> padded half)
+    monkeypatch.setenv("DYNA_MH_PACK16", "1")
+    rng = np.random.default_rng(n + n_hash)
+    sig = rng.integers(0, 6, size=(n, n_hash), dtype=np.uint32) * np.uint32(0x9E3779B1)
+    sig[rng.integers(0, n, 3)] = 0xFFFFFFFF
+    sig[:, 0] = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)  # an (almost) all-distinct row
+    want = port.mh_match_counts(sig)
+    assert (da.mh_match_counts(sig) == want).all()
+    monkeypatch.setenv("DYNA_MH_PACK16", "0")
+    assert (da.mh_match_counts(sig) == want).all()
+
+
+def test_16bit_path_overflow_falls_back_exactly(monkeypatch):
+    # more distinct values in a hash row than codes -> the gate sends the work to the 32-bit kernel
+    monkeypatch.setenv("DYNA_MH_PACK16", "1")
+    monkeypatch.setenv("DYNA_MH_MAXCODES", "5")
+    rng = np.random.default_rng(21)
+    sig = rng.integers(0, 9, size=(400, 33), dtype=np.uint32)
+    assert (da.mh_match_counts(sig) == port.mh_match_counts(sig)).all()
+    sig = rng.integers(0, 4, size=(400, 33), dtype=np.uint32)  # fits 5 codes: stays on the 16-bit kernel
+    assert (da.mh_match_counts(sig) == port.mh_match_counts(sig)).all()
+
+
+def test_similarityMH_large_default_path():
+    # n >= 2048 switches the 16-bit path on by default; row slabs through it as well
+    from dynaalign_b200 import synth
+    seqs = [s.decode() for s in synth.peptides_clustered(3000, children=20)]
+    seeds = port.hashfamily_seeds(42, 120)
+    sig = da.mh_signatures(seqs, 4, seeds)
+    assert (sig == port.mh_signatures(seqs, 4, seeds)).all()
+    want = port.mh_match_counts(sig)
+    assert (da.mh_match_counts(sig) == want).all()
+    assert want.max() > 60  # the clustered set really has matching pairs
+    b = da.partition_rows(3000, 3)
+    parts = [da.mh_match_counts(sig, int(b[s]), int(b[s + 1])) for s in range(3)]
+    assert (np.concatenate(parts) == want).all()
