@@ -24,7 +24,7 @@ from ._lib import DynaAlignError, check, flatten, lib, ptr
 __all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
            "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
            "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
-           "substitution_matrix", "DynaAlignError"]
+           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "DynaAlignError"]
 
 
 def dimnames(n):
@@ -129,6 +129,52 @@ def substitution_matrix(name):
     out = np.zeros((24, 24), dtype=np.int8)
     check(lib().dyna_substitution_matrix(name.encode(), ptr(out, C.c_int8)))
     return out
+
+
+# ----------------------------------------------------------------------------- threshold + sparsify (clusterbreak's next step)
+def quantile_type7_counts(hist, n_hash, prob):
+    """quantile(count/n_hash, prob, type=7) from the histogram of match counts -> (threshold, min_count)."""
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    thr, mc = C.c_double(0), C.c_int(0)
+    check(lib().dyna_quantile_type7_counts(ptr(hist, C.c_uint64), int(n_hash), float(prob), C.byref(thr), C.byref(mc)))
+    return thr.value, mc.value
+
+
+def similarityMH_edges(sequences, k=4, n_hash=50, thresh_p=0.8, *, seed=None, seeds=None, device=0):
+    """similarityMH followed by clusterbreak's thresholding (R/clusterbreak.R:217-221) without ever materialising the
+    dense n x n matrix:  threshold <- quantile(sim[upper.tri(sim)], thresh_p);  sim[sim < threshold] <- 0.
+    Returns (threshold, i, j, weight) with 0-based i < j in row-major order and weight = count / n_hash."""
+    sequences = list(sequences)
+    n = len(sequences)
+    res, off = flatten(sequences)
+    if n == 0:
+        raise DynaAlignError(L.ERR_INVALID, "Input sequences vector cannot be empty")
+    if seeds is None:
+        seeds = hashfamily_seeds(lib().dyna_random_seed() if seed is None else seed, n_hash)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    if k <= 0:
+        raise DynaAlignError(L.ERR_INVALID, "'k' must be a positive integer")
+    plan = lib().dyna_mh_plan_create(n, int(n_hash), 0, n, int(device))
+    if not plan:
+        raise DynaAlignError(L.ERR_CUDA, L.last_error())
+    try:
+        check(lib().dyna_mh_plan_upload_sequences(plan, ptr(res, C.c_uint8), ptr(off, C.c_int64), int(k), ptr(seeds, C.c_uint32), None))
+        check(lib().dyna_mh_plan_run_signatures(plan, None))
+        check(lib().dyna_mh_plan_run_match(plan, None))
+        hist = np.zeros(n_hash + 1, dtype=np.uint64)
+        check(lib().dyna_mh_plan_count_histogram(plan, ptr(hist, C.c_uint64), None))
+        thr, mc = quantile_type7_counts(hist, n_hash, thresh_p)
+        cap = int(hist[max(mc, 1):].sum())
+        ei = np.zeros(max(cap, 1), dtype=np.int32)
+        ej = np.zeros(max(cap, 1), dtype=np.int32)
+        ec = np.zeros(max(cap, 1), dtype=np.uint16)
+        ne = C.c_int64(0)
+        check(lib().dyna_mh_plan_threshold_edges(plan, mc, cap, ptr(ei, C.c_int32), ptr(ej, C.c_int32), ptr(ec, C.c_uint16),
+                                                 C.byref(ne), None))
+    finally:
+        lib().dyna_mh_plan_destroy(plan)
+    m = ne.value
+    return thr, ei[:m], ej[:m], ec[:m].astype(np.float64) / n_hash
 
 
 # ----------------------------------------------------------------------------- R pipeline (R/minHash.R)

@@ -286,6 +286,87 @@ extern "C" int dyna_mh_plan_fetch_counts(dyna_mh_plan* p, uint16_t* counts_out, 
   return DYNA_OK;
 }
 
+// ---- threshold + sparsify: the step right after the hot path in clusterbreak (R/clusterbreak.R:219-221)
+extern "C" int dyna_mh_plan_count_histogram(dyna_mh_plan* p, uint64_t* hist_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DevBuf<unsigned long long> d_hist;
+  DYNA_TRY(d_hist.alloc((size_t)p->n_hash + 1));
+  DYNA_TRY(launch_mh_count_hist(p->counts.p, p->pairs, p->n_hash, d_hist.p, st));
+  DYNA_CUDA(cudaMemcpyAsync(hist_out, d_hist.p, sizeof(uint64_t) * (size_t)(p->n_hash + 1), cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
+extern "C" int dyna_quantile_type7_counts(const uint64_t* hist, int n_hash, double prob, double* threshold_out, int* min_count_out) {
+  // R's quantile(x, prob, type = 7) (the default used at R/clusterbreak.R:219) for x = count / n_hash with the given
+  // multiplicities:  index = 1 + (N-1)*prob; lo = floor(index); hi = ceiling(index); qs = x[lo];
+  //                  if (index > lo && x[hi] != qs) qs = (1-h)*qs + h*x[hi], h = index - lo
+  if (n_hash <= 0 || !(prob >= 0.0 && prob <= 1.0)) return fail(DYNA_ERR_INVALID, "'probs' outside [0,1]");
+  long double total = 0;
+  for (int c = 0; c <= n_hash; ++c) total += (long double)hist[c];
+  if (total < 1) return fail(DYNA_ERR_INVALID, "quantile of an empty set of pairs");
+  const double N = (double)total;
+  const double index = 1.0 + std::max(N - 1.0, 0.0) * prob;
+  const double lo = std::floor(index), hi = std::ceil(index);
+  auto value_at_rank = [&](double r) {  // r-th smallest, 1-based
+    uint64_t cum = 0;
+    for (int c = 0; c <= n_hash; ++c) {
+      cum += hist[c];
+      if ((double)cum >= r) return static_cast<double>(c) / n_hash;
+    }
+    return 1.0;
+  };
+  double qs = value_at_rank(lo);
+  const double xhi = value_at_rank(hi);
+  if (index > lo && xhi != qs) {
+    const double h = index - lo;
+    qs = (1.0 - h) * qs + h * xhi;
+  }
+  if (threshold_out) *threshold_out = qs;
+  if (min_count_out) {  // `sim[sim < threshold] <- 0` keeps count/n_hash >= threshold
+    int c = 0;
+    while (c <= n_hash && static_cast<double>(c) / n_hash < qs) ++c;
+    *min_count_out = c;
+  }
+  return DYNA_OK;
+}
+
+extern "C" int dyna_mh_plan_threshold_edges(dyna_mh_plan* p, int min_count, int64_t max_edges, int32_t* i_out, int32_t* j_out,
+                                            uint16_t* count_out, int64_t* n_edges_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = p->row_end - p->row_begin;
+  if (n_edges_out) *n_edges_out = 0;
+  if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
+  const uint32_t mc = (uint32_t)std::max(min_count, 1);  // a zero count is never an edge (weight 0 in the adjacency matrix)
+  DevBuf<unsigned long long> rc, ro, tot;
+  DYNA_TRY(rc.alloc((size_t)rows));
+  DYNA_TRY(ro.alloc((size_t)rows));
+  DYNA_TRY(tot.alloc(1));
+  DYNA_TRY(launch_mh_edges_count(p->counts.p, p->n, p->row_begin, p->row_end, mc, rc.p, ro.p, tot.p, st));
+  unsigned long long total = 0;
+  DYNA_CUDA(cudaMemcpyAsync(&total, tot.p, sizeof total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  if (n_edges_out) *n_edges_out = (int64_t)total;
+  if ((int64_t)total > max_edges)
+    return fail(DYNA_ERR_INVALID, "edge buffer too small: %lld edges, capacity %lld", (long long)total, (long long)max_edges);
+  if (total == 0) return DYNA_OK;
+  DevBuf<int32_t> di, dj;
+  DevBuf<uint16_t> dc;
+  DYNA_TRY(di.alloc((size_t)total));
+  DYNA_TRY(dj.alloc((size_t)total));
+  DYNA_TRY(dc.alloc((size_t)total));
+  DYNA_TRY(launch_mh_edges_fill(p->counts.p, p->n, p->row_begin, p->row_end, mc, ro.p, di.p, dj.p, dc.p, st));
+  DYNA_CUDA(cudaMemcpyAsync(i_out, di.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaMemcpyAsync(j_out, dj.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaMemcpyAsync(count_out, dc.p, sizeof(uint16_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
 extern "C" int64_t dyna_mh_plan_pairs(const dyna_mh_plan* p) { return p ? p->pairs : 0; }
 extern "C" int dyna_mh_plan_launches(const dyna_mh_plan* p) { return p ? p->launches : 0; }
 extern "C" void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan* p) { return p ? p->counts.p : nullptr; }

@@ -587,6 +587,113 @@ __global__ void mh_expand_kernel(const uint16_t* __restrict__ counts, int64_t n,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// the step after the hot path (R/clusterbreak.R:219-221): threshold + sparsify.
+// Every similarity is count/n_hash, so quantile(sim[upper.tri], p) is exactly computable from the histogram of the
+// integer match counts, and `sim[sim < threshold] <- 0` becomes "keep pairs with count >= min_count".
+// ------------------------------------------------------------------------------------------------
+constexpr int kHistSmemBins = 8192;
+
+__global__ void __launch_bounds__(256)
+mh_count_hist_kernel(const uint16_t* __restrict__ counts, int64_t total, int nbins, unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t sh[kHistSmemBins];
+  const bool use_smem = nbins <= kHistSmemBins;
+  if (use_smem) {
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+  }
+  // 8 counts per 128-bit load on the aligned body, scalar head/tail
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(counts);
+  int64_t head = ((16 - (addr & 15)) & 15) / 2;
+  if (head > total) head = total;
+  const int64_t nvec = (total - head) / 8;
+  auto bump = [&](uint32_t c) {
+    if (use_smem) atomicAdd(&sh[c], 1u);
+    else atomicAdd(&hist[c], 1ull);
+  };
+  for (int64_t q = tid; q < head; q += nth) bump(counts[q]);
+  const uint4* v = reinterpret_cast<const uint4*>(counts + head);
+  for (int64_t q = tid; q < nvec; q += nth) {
+    const uint4 w = v[q];
+    bump(w.x & 0xFFFFu); bump(w.x >> 16); bump(w.y & 0xFFFFu); bump(w.y >> 16);
+    bump(w.z & 0xFFFFu); bump(w.z >> 16); bump(w.w & 0xFFFFu); bump(w.w >> 16);
+  }
+  for (int64_t q = head + nvec * 8 + tid; q < total; q += nth) bump(counts[q]);
+  if (use_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+      if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+  }
+}
+
+// one warp per matrix row: FILL = false counts the kept pairs of the row, FILL = true writes them (column order) at
+// the row's offset -> the edge list is deterministic (row-major), no global atomics
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+mh_edges_kernel(const uint16_t* __restrict__ counts, int64_t n, int64_t row_begin, int64_t row_end, int64_t slab_base,
+                uint32_t min_count, unsigned long long* __restrict__ row_counts, const unsigned long long* __restrict__ row_offsets,
+                int32_t* __restrict__ ei, int32_t* __restrict__ ej, uint16_t* __restrict__ ec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = row_begin + warp; i < row_end; i += nwarps) {
+    const uint16_t* row = counts + (i * n - i * (i + 1) / 2 - i - 1 - slab_base);  // + j
+    unsigned long long kept = 0;
+    unsigned long long base = FILL ? row_offsets[i - row_begin] : 0ull;
+    for (int64_t j0 = i + 1; j0 < n; j0 += 32) {
+      const int64_t j = j0 + lane;
+      const uint32_t c = j < n ? row[j] : 0u;
+      const bool keep = j < n && c >= min_count;
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+      if (FILL && keep) {
+        const unsigned long long pos = base + kept + __popc(m & ((1u << lane) - 1u));
+        ei[pos] = (int32_t)i;
+        ej[pos] = (int32_t)j;
+        ec[pos] = (uint16_t)c;
+      }
+      kept += __popc(m);
+    }
+    if (!FILL && lane == 0) row_counts[i - row_begin] = kept;
+  }
+}
+
+// exclusive scan of the per-row counts by a single block (rows <= a few hundred thousand)
+__global__ void __launch_bounds__(1024)
+mh_scan_rows_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, int64_t rows,
+                    unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long wtot[32];
+  __shared__ unsigned long long ctot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long running = 0;
+  for (int64_t base = 0; base < rows; base += 1024) {
+    const int64_t p = base + threadIdx.x;
+    const unsigned long long v = p < rows ? in[p] : 0ull;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = wtot[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, w, d);
+        if (lane >= d) w += t;
+      }
+      wtot[lane] = w;
+      if (lane == 31) ctot = w;
+    }
+    __syncthreads();
+    if (p < rows) out[p] = running + (warp ? wtot[warp - 1] : 0ull) + incl - v;
+    running += ctot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = running;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -759,6 +866,40 @@ int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int
   const int64_t slab_base = tri_strict_rows(n, row_begin);
   dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)std::min<int64_t>(row_end - row_begin, 32768));
   mh_expand_kernel<<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, slab_base, d_table, diag, d_out);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_count_hist(const uint16_t* d_counts, int64_t total, int n_hash, unsigned long long* d_hist, cudaStream_t st) {
+  DYNA_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)(n_hash + 1), st));
+  if (total <= 0) return DYNA_OK;
+  const int grid = (int)std::min<int64_t>((total + 2047) / 2048, (int64_t)kNumSMsB200 * 8);
+  mh_count_hist_kernel<<<grid, 256, 0, st>>>(d_counts, total, n_hash + 1, d_hist);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_edges_count(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, uint32_t min_count,
+                          unsigned long long* d_row_counts, unsigned long long* d_row_offsets, unsigned long long* d_total,
+                          cudaStream_t st) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0) return DYNA_OK;
+  const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMsB200 * 16);
+  mh_edges_kernel<false><<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, tri_strict_rows(n, row_begin), min_count,
+                                               d_row_counts, nullptr, nullptr, nullptr, nullptr);
+  DYNA_CUDA(cudaGetLastError());
+  mh_scan_rows_kernel<<<1, 1024, 0, st>>>(d_row_counts, d_row_offsets, rows, d_total);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_edges_fill(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, uint32_t min_count,
+                         const unsigned long long* d_row_offsets, int32_t* d_i, int32_t* d_j, uint16_t* d_c, cudaStream_t st) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0) return DYNA_OK;
+  const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMsB200 * 16);
+  mh_edges_kernel<true><<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, tri_strict_rows(n, row_begin), min_count,
+                                              nullptr, d_row_offsets, d_i, d_j, d_c);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }

@@ -132,6 +132,15 @@ DYNA_API int dyna_mh_plan_run_signatures(dyna_mh_plan*, void* stream); /* K1 + l
 DYNA_API int dyna_mh_plan_run_match(dyna_mh_plan*, void* stream);      /* K3 over the plan's row range */
 DYNA_API int dyna_mh_plan_fetch_signatures(dyna_mh_plan*, uint32_t* sig_out, void* stream);
 DYNA_API int dyna_mh_plan_fetch_counts(dyna_mh_plan*, uint16_t* counts_tri_out, void* stream);
+/* The step after the hot path in clusterbreak (R/clusterbreak.R:219-221), on the plan's device-resident counts:
+ *   threshold <- quantile(sim[upper.tri(sim)], thresh_p);  sim[sim < threshold] <- 0;  graph from the upper triangle.
+ * Similarities are count/n_hash, so the type-7 quantile is exact from the histogram of counts (sum the histograms of
+ * all row ranges first when the triangle is sharded), and the thresholded matrix is the edge list of pairs with
+ * count >= min_count (zero counts are never edges), emitted in row-major (i, then j) order. */
+DYNA_API int dyna_mh_plan_count_histogram(dyna_mh_plan*, uint64_t* hist_out /* n_hash+1 */, void* stream);
+DYNA_API int dyna_quantile_type7_counts(const uint64_t* hist, int n_hash, double prob, double* threshold_out, int* min_count_out);
+DYNA_API int dyna_mh_plan_threshold_edges(dyna_mh_plan*, int min_count, int64_t max_edges, int32_t* i_out, int32_t* j_out,
+                                 uint16_t* count_out, int64_t* n_edges_out, void* stream);
 DYNA_API int64_t dyna_mh_plan_pairs(const dyna_mh_plan*);
 DYNA_API int dyna_mh_plan_launches(const dyna_mh_plan*); /* kernels enqueued by the last run_* call */
 DYNA_API void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan*);

@@ -118,3 +118,19 @@ def test_rda_reader_on_reference_datasets():
         assert seqs == [ln.strip() for ln in f if ln.strip()]
     h3 = load_sequences("/root/reference/data/h3n2sample.rda", "sequence")
     assert len(h3) == 8103 and len(h3[0]) == 566
+
+
+def test_quantile_type7_from_histogram_matches_r_definition():
+    from oracle.quantile_r import quantile_type7
+    rng = np.random.default_rng(9)
+    for n_hash in (1, 7, 50, 500):
+        for _ in range(20):
+            counts = rng.integers(0, n_hash + 1, size=int(rng.integers(1, 400)))
+            hist = np.bincount(counts, minlength=n_hash + 1).astype(np.uint64)
+            for p in (0.0, 0.1, 0.5, 0.8, 0.999, 1.0, float(rng.random())):
+                thr, mc = da.quantile_type7_counts(hist, n_hash, p)
+                assert thr == quantile_type7(counts / n_hash, p)
+                kept = counts / n_hash >= thr
+                assert ((counts >= mc) == kept).all()
+    with pytest.raises(da.DynaAlignError):
+        da.quantile_type7_counts(np.zeros(5, np.uint64), 4, 0.5)

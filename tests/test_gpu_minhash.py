@@ -170,3 +170,19 @@ def test_similarityMH_large_default_path():
     b = da.partition_rows(3000, 3)
     parts = [da.mh_match_counts(sig, int(b[s]), int(b[s + 1])) for s in range(3)]
     assert (np.concatenate(parts) == want).all()
+
+
+@pytest.mark.parametrize("p", [0.0, 0.25, 0.8, 0.9371, 1.0])
+def test_threshold_and_edge_list(p, evp):
+    # clusterbreak's step after sim_fn (R/clusterbreak.R:219-221) from the device-resident counts
+    from oracle.quantile_r import quantile_type7
+    full = port.similarityMH(evp, 2, 50, 42)
+    iu = np.triu_indices(len(evp), 1)
+    want_thr = quantile_type7(full[iu], p)
+    thr, ei, ej, w = da.similarityMH_edges(evp, 2, 50, p, seed=42)
+    assert thr == want_thr
+    assert abs(thr - np.quantile(full[iu], p)) < 1e-12  # numpy's "linear" method is type 7 up to rounding
+    dense = full.copy()
+    dense[dense < want_thr] = 0.0  # pep.sim[pep.sim < threshold] <- 0
+    wi, wj = np.nonzero(np.triu(dense, 1))
+    assert (ei == wi).all() and (ej == wj).all() and (w == dense[wi, wj]).all()

@@ -39,7 +39,7 @@ def to_bytes(v, unit):
 
 os.makedirs(OUT, exist_ok=True)
 traffic = {}
-for name in ("nw_prof", "mh_prof"):
+for name in ("nw_prof", "mh_prof", "nw2_prof", "mh2_prof"):
     rep = os.path.join(G, name + ".ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -56,13 +56,13 @@ for name in ("nw_prof", "mh_prof"):
     best = max(rows, key=lambda r: float(r[idx["gpu__time_duration.sum"]]))
     dram = to_bytes(best[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
         to_bytes(best[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
-    key = "nw_warp_kernel_dram_bytes_per_launch" if name == "nw_prof" else "mh_match_kernel_dram_bytes_per_launch"
+    key = "nw_warp_kernel_dram_bytes_per_launch" if name.startswith("nw") else "mh_match_kernel_dram_bytes_per_launch"
     traffic[key] = dram
     traffic[key + "_kernel"] = best[idx["Kernel Name"]]
     traffic[key + "_grid"] = best[idx["Grid Size"]] if "Grid Size" in idx else None
 if traffic:
     traffic["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/prof_target.py: NW n=700 "
-                       "families, MinHash n=16384); the capture is a reduced workload, so bytes are per THAT launch")
+                       "families, MinHash n=32768 -> 536,854,528 pairs); the capture is a reduced workload, so bytes are per THAT launch")
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)
 
