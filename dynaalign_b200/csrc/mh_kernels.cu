@@ -809,12 +809,9 @@ static int match_geometry(int64_t n, int64_t row_begin, int64_t row_end, int64_t
 static int ensure_tma_smem() {
   const size_t smem = kMatchStages * sizeof(MatchStage) + kMatchStages * sizeof(uint64_t);
   static_assert(kMatchStages * sizeof(MatchStage) >= sizeof(uint16_t) * kMatchBM * kCsPitch, "staging tile must fit the ring");
-  static bool attr_done = false;
-  if (!attr_done) {
-    DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  // the attribute is per device (and the library may drive several devices from one process): set it every time
+  DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DYNA_CUDA(cudaFuncSetAttribute(mh_match_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return DYNA_OK;
 }
 
