@@ -380,7 +380,7 @@ extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
 // NW plan
 // =====================================================================================================
 struct NwClass {
-  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp kernel multipass, 4 two-pairs-per-warp 16-bit kernel
+  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit
   int R;
   std::vector<NwUnit> units;
   DevBuf<NwUnit> d_units;
@@ -459,7 +459,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
   auto fits16 = [&](int m) {
     const int64_t hi = (int64_t)std::max(smax, 0) * std::min<int64_t>(m, max_len) + ((int64_t)m + max_len) * gap_ext + gap_open;
-    return pack16 && m > kNwThreadMaxRows && m <= 32 * kNwWarp2MaxR && hi <= 32000 && (int64_t)m + max_len <= 65535;
+    return pack16 && m <= 32 * kNwWarp2MaxR && hi <= 32000 && (int64_t)m + max_len <= 65535;
   };
 
   // encode residues, 32-bit offsets
@@ -496,6 +496,8 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     const int m = (int)(offsets[i + 1] - offsets[i]);
     int kind, R, step;
     if (m == 0) { kind = 0; R = 0; step = 4096; }
+    else if (getenv("DYNA_NW_FORCE_WARP2") && fits16(m)) { kind = 4; R = std::max(2, nw_warp_R(m)); step = 2 * kNwWarpUnitPairs; }
+    else if (nw_use_thread_kernel(m) && fits16(m)) { kind = 5; R = nw_thread_R(m); step = 2 * kNwThreadUnitPairs; }
     else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
     else if (fits16(m)) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
     else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
@@ -549,6 +551,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       case 1: DYNA_TRY(launch_nw_thread(c->R, p->slant, d, c->d_units.p, nu, st)); break;
       case 2: DYNA_TRY(launch_nw_warp(c->R, p->slant, false, d, c->d_units.p, nu, nullptr, 0, st)); break;
       case 4: DYNA_TRY(launch_nw_warp2(c->R, d, c->d_units.p, nu, st)); break;
+      case 5: DYNA_TRY(launch_nw_thread2(c->R, d, c->d_units.p, nu, st)); break;
       default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, st)); break;
     }
     ++p->launches;

@@ -557,6 +557,101 @@ nw_thread_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4x2: one thread per TWO pairs (rows <= 32), 16-bit lanes -- the short-probe kernel with the same s16x2 packing
+// as nw_warp2_kernel: a thread walks two column sequences against the CTA's row sequence, pair A in the low halves,
+// pair B in the high halves.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kThreadThreads)
+nw_thread2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  using S = Strip<R>;
+  __shared__ uint32_t prof[25 * S::RWS];  // class 24 = padding residue
+  const int tid = threadIdx.x;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.one - 1u;
+  // The sentinel must live in a register the compiler cannot see through: with an immediate operand ptxas commutes
+  // VIMNMX.S16x2 and the ">=" predicates it returns come back with the wrong sense (observed with CUDA 12.9:
+  // the first DP row then takes 'U' where it must take 'L').  "+ opaque zero" keeps it a plain register operand.
+  const uint32_t sent2 = pack16(kSentinel16) + c.zero;
+  const uint32_t bord2 = pack16(ge - go);
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row;
+    const int m = d.off[row + 1] - d.off[row];
+    __syncthreads();
+    build_profile<R, 1>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, kThreadThreads);
+    for (int idx = tid; idx < S::RWS; idx += kThreadThreads) prof[24 * S::RWS + idx] = 0u;
+    __syncthreads();
+    const int npairs2 = (un.j_count + 1) >> 1;
+    for (int pp = tid; pp < npairs2; pp += kThreadThreads) {
+      int jA = un.j_begin + 2 * pp;
+      int jB = jA + 1;
+      const bool hasB = (jB < un.j_begin + un.j_count);
+      if (!hasB) jB = jA;
+      int nA = d.off[jA + 1] - d.off[jA], nB = d.off[jB + 1] - d.off[jB];
+      if (nB > nA) {
+        int tj = jA; jA = jB; jB = tj;
+        int tn = nA; nA = nB; nB = tn;
+      }
+      const uint8_t* __restrict__ bA = d.codes + d.off[jA];
+      const uint8_t* __restrict__ bB = d.codes + d.off[jB];
+      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        H0[k] = H1[k] = bord2;
+        El[k] = sent2;
+        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+      }
+      uint32_t diagH = 0u;  // corner (0,0)
+      uint32_t resB = 0u, outF;
+      for (int t0 = 0; t0 < nA; t0 += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const int t = t0 + ph;
+          if (t < nA) {
+            const int cA = bA[t];
+            const int cB = (t < nB) ? (int)bB[t] : 24;
+            uint32_t pwA[S::RW], pwB[S::RW];
+#pragma unroll
+            for (int w = 0; w < S::RW; ++w) {
+              pwA[w] = prof[cA * S::RWS + w];
+              pwB[w] = prof[cB * S::RWS + w];
+            }
+            if (ph == 0)
+              strip_column2<R, 1>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, diagH, 0u, 0u, sent2, 0u, 0u, ngo2, c, outF);
+            else
+              strip_column2<R, 1>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, diagH, 0u, 0u, sent2, 0u, 0u, ngo2, c, outF);
+            diagH = bord2;  // border row, slanted: -go + ge for every column >= 1
+            if (t == nB - 1) {
+#pragma unroll
+              for (int k = 0; k < R; ++k)
+                if (k == m - 1) resB = (ph == 0) ? SB1[k] : SB0[k];
+            }
+          }
+        }
+      }
+      const bool in1 = ((nA & 1) != 0);
+      uint32_t resA = 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (k == m - 1) resA = in1 ? SA1[k] : SA0[k];
+      const int64_t slotA = pair_slot(d.n, row, jA, d.slab_base);
+      d.matches[slotA] = resA >> 16;
+      d.length[slotA] = (uint32_t)(m + nA) - (resA & 0xFFFFu);
+      if (hasB) {
+        const int64_t slotB = pair_slot(d.n, row, jB, d.slab_base);
+        d.matches[slotB] = resB >> 16;
+        d.length[slotB] = (uint32_t)(m + nB) - (resB & 0xFFFFu);
+      }
+    }
+  }
+}
+
 // rows of length 0: no DP; the path is n left moves -> matches 0, length n (0/0 -> NaN handled at the division)
 __global__ void nw_empty_rows_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -655,6 +750,22 @@ int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, con
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw warp kernel: unsupported strip height %d", R);
   }
+}
+
+int launch_nw_thread2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR)                                                                  \
+  case RR:                                                                             \
+    nw_thread2_kernel<RR><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units); \
+    break;
+    DYNA_CASE(4) DYNA_CASE(8) DYNA_CASE(12) DYNA_CASE(16) DYNA_CASE(20) DYNA_CASE(24) DYNA_CASE(28) DYNA_CASE(32)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw thread2 kernel: unsupported strip height %d", R);
+  }
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
 }
 
 int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {

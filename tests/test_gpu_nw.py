@@ -164,3 +164,17 @@ def test_packed16_range_guard():
     seqs = ["W" * 640, "W" * 600, "W" * 64 + "A" * 500, "C" * 640]
     check_stats(seqs, "BLOSUM100", 1, 30)
     check_stats(seqs, "BLOSUM62", 10, 4)
+
+
+def test_short_rows_against_longer_columns_many_shapes():
+    # regression: the two-pairs-per-thread kernel once took 'U' for 'L' in the first DP row (compiler commuted a
+    # VIMNMX.S16x2 with an immediate operand); single row sequence vs one or two column sequences of any length
+    rng = np.random.default_rng(5)
+    for trial in range(250):
+        m, n = int(rng.integers(1, 33)), int(rng.integers(0, 60))
+        seqs = random_seqs(rng, 1, m, m) + random_seqs(rng, 1 + trial % 2, n, n)
+        go, ge = int(rng.integers(0, 13)), int(rng.integers(0, 6))
+        name = TABLES[trial % 6]
+        gm, gl = da.nw_pair_stats(seqs, name, go, ge)
+        wm, wl = port.nw_pair_stats(seqs, name, go, ge)
+        assert (gm == wm).all() and (gl == wl).all(), (seqs, name, go, ge)

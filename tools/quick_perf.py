@@ -59,7 +59,12 @@ def mh(n, n_hash=500, k=4, mode=None):
 
 
 def nw(n, kind="families"):
-    seqs = synth.proteins_families(n) if kind == "families" else synth.proteins_uniform(n)
+    if kind == "pep12":
+        seqs = synth.peptides_uniform(n, length=12)
+    elif kind == "pep16":
+        seqs = synth.peptides_uniform(n, length=16)
+    else:
+        seqs = synth.proteins_families(n) if kind == "families" else synth.proteins_uniform(n)
     res, off = flatten(seqs)
     t0 = time.time()
     p = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, 0, n, 0)
@@ -88,3 +93,6 @@ if __name__ == "__main__":
         nw(2000, "uniform")
     if "nwbig" in what:
         nw(5000)
+    if "nwpep" in what:
+        nw(20000, "pep12")
+        nw(20000, "pep16")
