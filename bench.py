@@ -381,6 +381,11 @@ def main():
         cpu_mh = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
                   "sample": "reference similarityMH on the first 4000 peptides of config 4 (%d pairs, %.1f s), OpenMP on all host cores" % (pairs, dt)}
 
+    # ================================================================== BASELINE configs 1-3 through the drop-in API (rank 0)
+    other = None
+    if rank == 0:
+        other = small_configs(dev)
+
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     tinfo = {}
@@ -406,7 +411,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "int32_issue", "achieved": achieved / 1e9, "peak": int_peak / 1e9, "unit": "Gop/s",
                          "frac": achieved / int_peak, "traffic": traffic,
-                         "note": "dominant kernel nw_warp_kernel: neither HBM- nor tensor-bound; 11 algorithmic integer ops per DP cell "
+                         "note": "dominant kernel nw_warp2_kernel (16-bit DPX, two pairs per warp): neither HBM- nor tensor-bound; 11 algorithmic integer ops per DP cell "
                                  "(SURVEY.md 8(d)) against the INT32 issue peak measured live by dyna_probe_int_issue (IADD3 chains)"},
             "cpu_baseline": cpu,
             "minhash": {
@@ -429,10 +434,51 @@ def main():
                 "cpu_baseline": cpu_mh,
             },
             "int32_issue_peak_lane_ops_per_s": int_peak,
+            "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_configs(dev):
+    """BASELINE configs 1, 2 and the sim_fn of config 3 on the reference's own data (fixtures under tests/golden),
+    end to end through the drop-in entry points: host strings in, host n x n double matrix out."""
+    import gzip
+
+    import dynaalign_b200 as da
+    gdir = os.path.join(ROOT, "tests", "golden")
+    try:
+        with open(os.path.join(gdir, "evp_probe_sequences.txt")) as f:
+            evp = [ln.strip() for ln in f if ln.strip()]
+        with gzip.open(os.path.join(gdir, "h3n2sample_first1000.json.gz"), "rt") as f:
+            d = json.load(f)
+        h3 = [d["unique"][i] for i in d["index"]]
+    except OSError:
+        return None
+
+    def best_of(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    out = {}
+    t = best_of(lambda: da.similarityMH(evp, 2, 50, seed=42))
+    out["config1_similarityMH_evp_k2_h50"] = {"n": len(evp), "seconds": t, "pairs_per_s": len(evp) * (len(evp) - 1) / 2 / t}
+    lens = np.array([len(s) for s in h3], dtype=np.int64)
+    cells = int((lens * np.cumsum(lens[::-1])[::-1]).sum())
+    t = best_of(lambda: da.similarityNW(h3))
+    out["config2_similarityNW_h3n2_1000"] = {"n": len(h3), "cells": cells, "seconds": t, "gcups": cells / t / 1e9}
+    t = best_of(lambda: da.similarityMH(h3, 4, 500, seed=42))
+    out["config3_simfn_similarityMH_h3n2_1000_k4_h500"] = {"n": len(h3), "seconds": t,
+                                                            "pairs_per_s": len(h3) * (len(h3) - 1) / 2 / t}
+    out["note"] = ("wall clock of the drop-in call (flatten + validate + H2D + kernels + expansion to the column-major double matrix "
+                   "+ D2H), best of 3; inputs are the reference's evp_peparray / h3n2sample extracts")
+    return out
 
 
 def mh_hrows(n_hash):
