@@ -363,13 +363,16 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
   outF = F;
 }
 
-template <int R, int VAR>
-__global__ void __launch_bounds__(kWarpThreads)
+// INPLACE: one register set for (H, S) instead of the ping-pong pair -- 4R instead of 7R state registers at the price
+// of three register moves per row (they issue as IMAD.MOV, off the ALU pipe).  Used for tall strips (R >= 13), where
+// the ping-pong version drops to one CTA per SM.
+template <int R, int VAR, bool INPLACE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   using S = Strip<R>;
   __shared__ uint32_t prof[25 * 32 * S::RWS];  // class 24 = padding residue, all-zero entries
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int nwarps = kWarpThreads / 32;
+  constexpr int nwarps = THREADS / 32;
   const int go = d.gap_open, ge = d.gap_ext;
   const uint32_t ngo2 = pack16(-go);
   const uint32_t sent2 = pack16(kSentinel16);
@@ -384,8 +387,8 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int row = un.row;
     const int m = d.off[row + 1] - d.off[row];
     __syncthreads();
-    build_profile<R, 32>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, kWarpThreads);
-    for (int idx = tid; idx < 32 * S::RWS; idx += kWarpThreads) prof[24 * 32 * S::RWS + idx] = 0u;
+    build_profile<R, 32>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
+    for (int idx = tid; idx < 32 * S::RWS; idx += THREADS) prof[24 * 32 * S::RWS + idx] = 0u;
     __syncthreads();
     const int lm = (m - 1) / R;
     const int km = (m - 1) - lm * R;
@@ -405,12 +408,17 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       const uint8_t* __restrict__ bA = d.codes + d.off[jA];
       const uint8_t* __restrict__ bB = d.codes + d.off[jB];
 
-      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+      constexpr int R2 = INPLACE ? 1 : R;  // second register set only for the ping-pong version
+      uint32_t H0[R], H1[R2], El[R], SA0[R], SA1[R2], SB0[R], SB1[R2];
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        H0[k] = H1[k] = bord2;
+        H0[k] = bord2;
         El[k] = sent2;
-        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;  // border column: no diagonal step yet
+        SA0[k] = SB0[k] = 0u;  // border column: no diagonal step yet
+        if (!INPLACE) {
+          H1[k] = bord2;
+          SA1[k] = SB1[k] = 0u;
+        }
       }
       uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
       uint32_t prevUpSA = 0u, prevUpSB = 0u;
@@ -443,7 +451,13 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
               pwA[w] = pa[w];
               pwB[w] = pb[w];
             }
-            if (ph == 0) {
+            if constexpr (INPLACE) {
+              strip_column2<R, VAR>(H0, H0, El, SA0, SA0, SB0, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                    ngo2, c, outF);
+              outH = H0[R - 1];
+              outSA = SA0[R - 1];
+              outSB = SB0[R - 1];
+            } else if (ph == 0) {
               strip_column2<R, VAR>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
                                     ngo2, c, outF);
               outH = H1[R - 1];
@@ -462,7 +476,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
             if (lane == lm && jc == nB - 1) {  // the shorter sequence ends here: capture its result
 #pragma unroll
               for (int k = 0; k < R; ++k)
-                if (k == km) resB = (ph == 0) ? SB1[k] : SB0[k];
+                if (k == km) resB = (!INPLACE && ph == 0) ? SB1[INPLACE ? 0 : k] : SB0[k];
             }
           }
         }
@@ -471,7 +485,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       uint32_t resA = 0u;
 #pragma unroll
       for (int k = 0; k < R; ++k)
-        if (k == km) resA = in1 ? SA1[k] : SA0[k];
+        if (k == km) resA = (!INPLACE && in1) ? SA1[INPLACE ? 0 : k] : SA0[k];
       resA = __shfl_sync(full, resA, lm);
       resB = __shfl_sync(full, resB, lm);
       if (lane == 0) {
@@ -689,8 +703,11 @@ int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int 
 template <int R>
 int launch_warp2_R(int var, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   // variant 0 (A/B measurements) is only instantiated for the strip heights of the benchmark proteins
-  if (var == 0 && R >= 10 && R <= 12) nw_warp2_kernel<(R >= 10 && R <= 12) ? R : 10, 0><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
-  else nw_warp2_kernel<R, 1><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
+  int inplace_min_r = 13;
+  if (const char* e = getenv("DYNA_NW2_INPLACE_MINR")) inplace_min_r = atoi(e);
+  if (var == 0 && R >= 10 && R <= 12) nw_warp2_kernel<(R >= 10 && R <= 12) ? R : 10, 0, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
+  else if (R >= inplace_min_r) nw_warp2_kernel<R, 1, true, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);  // tall strips: 4-warp CTAs, 3 per SM
+  else nw_warp2_kernel<R, 1, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }
