@@ -54,6 +54,7 @@ _SIGS = {
     "dyna_mh_plan_run_match": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dyna_mh_plan_fetch_signatures": (C.c_int, [C.c_void_p, _u32p, C.c_void_p]),
     "dyna_mh_plan_fetch_counts": (C.c_int, [C.c_void_p, _u16p, C.c_void_p]),
+    "dyna_mh_plan_create_subset": (C.c_void_p, [C.c_void_p, _i64p, C.c_int64, C.c_int64, C.c_int64]),
     "dyna_mh_plan_count_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "dyna_quantile_type7_counts": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_double, _f64p, C.POINTER(C.c_int)]),
     "dyna_mh_plan_threshold_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _u16p, _i64p, C.c_void_p]),

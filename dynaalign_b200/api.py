@@ -24,7 +24,7 @@ from ._lib import DynaAlignError, check, flatten, lib, ptr
 __all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
            "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
            "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
-           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "DynaAlignError"]
+           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "DynaAlignError"]
 
 
 def dimnames(n):
@@ -175,6 +175,87 @@ def similarityMH_edges(sequences, k=4, n_hash=50, thresh_p=0.8, *, seed=None, se
         lib().dyna_mh_plan_destroy(plan)
     m = ne.value
     return thr, ei[:m], ej[:m], ec[:m].astype(np.float64) / n_hash
+
+
+class MinHashPlan:
+    """Device-resident MinHash state for one set of sequences: hash once, then match, threshold and recurse into
+    sub-clusters (clusterbreak's loop, R/clusterbreak.R:203-259) without leaving the GPU or re-hashing."""
+
+    _matched = False
+
+    def __init__(self, sequences=None, k=4, n_hash=50, *, seed=None, seeds=None, device=0, _handle=None, _n=None):
+        self.n_hash = int(n_hash)
+        if _handle is not None:
+            self._h, self.n = _handle, _n
+            return
+        sequences = list(sequences)
+        self.n = len(sequences)
+        if self.n == 0:
+            raise DynaAlignError(L.ERR_INVALID, "Input sequences vector cannot be empty")
+        if k <= 0:
+            raise DynaAlignError(L.ERR_INVALID, "'k' must be a positive integer")
+        if n_hash <= 0:
+            raise DynaAlignError(L.ERR_INVALID, "Number of hash functions must be positive")
+        if seeds is None:
+            seeds = hashfamily_seeds(lib().dyna_random_seed() if seed is None else seed, n_hash)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        res, off = flatten(sequences)
+        self._h = lib().dyna_mh_plan_create(self.n, self.n_hash, 0, self.n, int(device))
+        if not self._h:
+            raise DynaAlignError(L.ERR_CUDA, L.last_error())
+        check(lib().dyna_mh_plan_upload_sequences(self._h, ptr(res, C.c_uint8), ptr(off, C.c_int64), int(k), ptr(seeds, C.c_uint32), None))
+        check(lib().dyna_mh_plan_run_signatures(self._h, None))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dyna_mh_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _match(self):
+        if not self._matched:
+            check(lib().dyna_mh_plan_run_match(self._h, None))
+            self._matched = True
+
+    def signatures(self):
+        out = np.zeros((self.n, self.n_hash), dtype=np.uint32)
+        check(lib().dyna_mh_plan_fetch_signatures(self._h, ptr(out, C.c_uint32), None))
+        return out
+
+    def match_counts(self):
+        self._match()
+        out = np.zeros(max(tri_strict_size(self.n), 1), dtype=np.uint16)
+        check(lib().dyna_mh_plan_fetch_counts(self._h, ptr(out, C.c_uint16), None))
+        return out[:tri_strict_size(self.n)]
+
+    def histogram(self):
+        self._match()
+        hist = np.zeros(self.n_hash + 1, dtype=np.uint64)
+        check(lib().dyna_mh_plan_count_histogram(self._h, ptr(hist, C.c_uint64), None))
+        return hist
+
+    def threshold_edges(self, thresh_p):
+        """(threshold, i, j, weight): quantile(sim[upper.tri], thresh_p) and the pairs with sim >= threshold (sim > 0)."""
+        hist = self.histogram()
+        thr, mc = quantile_type7_counts(hist, self.n_hash, thresh_p)
+        cap = int(hist[max(mc, 1):].sum())
+        ei = np.zeros(max(cap, 1), dtype=np.int32)
+        ej = np.zeros(max(cap, 1), dtype=np.int32)
+        ec = np.zeros(max(cap, 1), dtype=np.uint16)
+        ne = C.c_int64(0)
+        check(lib().dyna_mh_plan_threshold_edges(self._h, mc, cap, ptr(ei, C.c_int32), ptr(ej, C.c_int32), ptr(ec, C.c_uint16),
+                                                 C.byref(ne), None))
+        m = ne.value
+        return thr, ei[:m], ej[:m], ec[:m].astype(np.float64) / self.n_hash
+
+    def subset(self, indices):
+        """Plan over sequences[indices] (0-based), reusing this plan's signatures."""
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        h = lib().dyna_mh_plan_create_subset(self._h, ptr(idx, C.c_int64), len(idx), 0, len(idx))
+        if not h:
+            raise DynaAlignError(L.ERR_INVALID, L.last_error())
+        return MinHashPlan(n_hash=self.n_hash, _handle=h, _n=len(idx))
 
 
 # ----------------------------------------------------------------------------- R pipeline (R/minHash.R)

@@ -286,6 +286,38 @@ extern "C" int dyna_mh_plan_fetch_counts(dyna_mh_plan* p, uint16_t* counts_out, 
   return DYNA_OK;
 }
 
+// ---- sub-cluster plans: clusterbreak calls sim_fn again on every oversized cluster (R/clusterbreak.R:250-254); the
+// signatures of a subset are a subset of the signatures, so the child plan gathers rows instead of re-hashing
+extern "C" dyna_mh_plan* dyna_mh_plan_create_subset(dyna_mh_plan* parent, const int64_t* indices, int64_t m, int64_t row_begin,
+                                                    int64_t row_end) {
+  if (!parent || !parent->have_sig || !indices || m <= 0) {
+    fail(DYNA_ERR_INVALID, "dyna_mh_plan_create_subset: parent has no signatures or bad arguments");
+    return nullptr;
+  }
+  for (int64_t r = 0; r < m; ++r)
+    if (indices[r] < 0 || indices[r] >= parent->n) {
+      fail(DYNA_ERR_INVALID, "dyna_mh_plan_create_subset: index %lld out of range", (long long)indices[r]);
+      return nullptr;
+    }
+  dyna_mh_plan* c = dyna_mh_plan_create(m, parent->n_hash, row_begin, row_end, parent->device);
+  if (!c) return nullptr;
+  DevBuf<int64_t> d_idx;
+  int rc = d_idx.alloc((size_t)m);
+  if (rc == DYNA_OK && cudaMemcpy(d_idx.p, indices, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: host-to-device copy failed");
+  if (rc == DYNA_OK) rc = launch_mh_gather_rows(parent->sig.p, d_idx.p, m, parent->n_hash, c->sig.p, nullptr);
+  int l = 0;
+  if (rc == DYNA_OK) rc = mh_plan_prepare_match_inputs(c, nullptr, &l);
+  if (rc == DYNA_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: subset gather failed");
+  if (rc != DYNA_OK) {
+    dyna_mh_plan_destroy(c);
+    return nullptr;
+  }
+  c->have_sig = c->have_sigT = true;
+  c->launches = 1 + l;
+  return c;
+}
+
 // ---- threshold + sparsify: the step right after the hot path in clusterbreak (R/clusterbreak.R:219-221)
 extern "C" int dyna_mh_plan_count_histogram(dyna_mh_plan* p, uint64_t* hist_out, void* stream) {
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");

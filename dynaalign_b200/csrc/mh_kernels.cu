@@ -587,6 +587,17 @@ __global__ void mh_expand_kernel(const uint16_t* __restrict__ counts, int64_t n,
   }
 }
 
+// gather of signature rows for a sub-cluster (clusterbreak re-invokes sim_fn on subsets, R/clusterbreak.R:250-254):
+// the signatures of a subset are the subset of the signatures, so nothing is re-hashed
+__global__ void mh_gather_rows_kernel(const uint32_t* __restrict__ sig, const int64_t* __restrict__ idx, int64_t m, int n_hash,
+                                      uint32_t* __restrict__ out) {
+  for (int64_t r = blockIdx.x; r < m; r += gridDim.x) {
+    const uint32_t* src = sig + idx[r] * (int64_t)n_hash;
+    uint32_t* dst = out + r * (int64_t)n_hash;
+    for (int h = threadIdx.x; h < n_hash; h += blockDim.x) dst[h] = src[h];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the step after the hot path (R/clusterbreak.R:219-221): threshold + sparsify.
 // Every similarity is count/n_hash, so quantile(sim[upper.tri], p) is exactly computable from the histogram of the
@@ -897,6 +908,13 @@ int launch_mh_edges_fill(const uint16_t* d_counts, int64_t n, int64_t row_begin,
   const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMsB200 * 16);
   mh_edges_kernel<true><<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, tri_strict_rows(n, row_begin), min_count,
                                               nullptr, d_row_offsets, d_i, d_j, d_c);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_mh_gather_rows(const uint32_t* d_sig, const int64_t* d_idx, int64_t m, int n_hash, uint32_t* d_out, cudaStream_t st) {
+  if (m <= 0) return DYNA_OK;
+  mh_gather_rows_kernel<<<(int)std::min<int64_t>(m, (int64_t)kNumSMsB200 * 16), 128, 0, st>>>(d_sig, d_idx, m, n_hash, d_out);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }

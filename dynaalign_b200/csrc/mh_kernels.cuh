@@ -54,6 +54,7 @@ int launch_mh_relabel(const uint32_t* d_sigT, int64_t n, int n_hash, int64_t npi
 int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,
                      double diag, double* d_out, cudaStream_t st);
 
+int launch_mh_gather_rows(const uint32_t* d_sig, const int64_t* d_idx, int64_t m, int n_hash, uint32_t* d_out, cudaStream_t st);
 // threshold + sparsify (R/clusterbreak.R:219-221) on the counts slab
 int launch_mh_count_hist(const uint16_t* d_counts, int64_t total, int n_hash, unsigned long long* d_hist, cudaStream_t st);
 int launch_mh_edges_count(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, uint32_t min_count,

@@ -132,6 +132,11 @@ DYNA_API int dyna_mh_plan_run_signatures(dyna_mh_plan*, void* stream); /* K1 + l
 DYNA_API int dyna_mh_plan_run_match(dyna_mh_plan*, void* stream);      /* K3 over the plan's row range */
 DYNA_API int dyna_mh_plan_fetch_signatures(dyna_mh_plan*, uint32_t* sig_out, void* stream);
 DYNA_API int dyna_mh_plan_fetch_counts(dyna_mh_plan*, uint16_t* counts_tri_out, void* stream);
+/* Child plan over a subset of the parent's sequences (clusterbreak's recursion re-invokes sim_fn on each oversized
+ * cluster, R/clusterbreak.R:250-254): gathers the parent's device-resident signature rows, nothing is re-hashed.
+ * indices[m] are 0-based positions in the parent; the child is independent of the parent afterwards. */
+DYNA_API dyna_mh_plan* dyna_mh_plan_create_subset(dyna_mh_plan* parent, const int64_t* indices, int64_t m, int64_t row_begin,
+                                         int64_t row_end);
 /* The step after the hot path in clusterbreak (R/clusterbreak.R:219-221), on the plan's device-resident counts:
  *   threshold <- quantile(sim[upper.tri(sim)], thresh_p);  sim[sim < threshold] <- 0;  graph from the upper triangle.
  * Similarities are count/n_hash, so the type-7 quantile is exact from the histogram of counts (sum the histograms of

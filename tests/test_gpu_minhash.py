@@ -186,3 +186,22 @@ def test_threshold_and_edge_list(p, evp):
     dense[dense < want_thr] = 0.0  # pep.sim[pep.sim < threshold] <- 0
     wi, wj = np.nonzero(np.triu(dense, 1))
     assert (ei == wi).all() and (ej == wj).all() and (w == dense[wi, wj]).all()
+
+
+def test_plan_subsets_reuse_signatures(evp):
+    # clusterbreak's recursion: sim_fn on a sub-cluster == the sub-matrix of match counts, without re-hashing
+    from oracle.quantile_r import quantile_type7
+    plan = da.MinHashPlan(evp, 2, 50, seed=42)
+    full = port.similarityMH(evp, 2, 50, 42)
+    rng = np.random.default_rng(4)
+    for size in (2, 37, 300):
+        idx = np.sort(rng.choice(len(evp), size=size, replace=False))
+        sub = plan.subset(idx)
+        counts = sub.match_counts()
+        want = np.rint(full[np.ix_(idx, idx)][np.triu_indices(size, 1)] * 50).astype(np.uint16)
+        assert (counts == want).all()
+        thr, ei, ej, w = sub.threshold_edges(0.8)
+        assert thr == quantile_type7(full[np.ix_(idx, idx)][np.triu_indices(size, 1)], 0.8)
+        sub.close()
+    assert (plan.signatures() == port.mh_signatures(evp, 2, port.hashfamily_seeds(42, 50))).all()
+    plan.close()
