@@ -43,6 +43,7 @@ _SIGS = {
     "dyna_mh_match_matrix": (C.c_int, [_u32p, C.c_int64, C.c_int, C.c_int, _f64p, C.c_int]),
     "dyna_similarityMH": (C.c_int, [_u8p, _i64p, C.c_int64, C.c_int, C.c_int, _u32p, _f64p, C.c_int]),
     "dyna_mh_signatures_linear": (C.c_int, [_i32p, _i64p, C.c_int64, _i64p, _i64p, C.c_int64, C.c_int, _u32p]),
+    "dyna_minhash_vocab_ranks": (C.c_int, [_u8p, _i64p, C.c_int64, C.c_int, C.POINTER(C.c_uint64), C.c_int64, _i64p, _i32p, _i64p]),
     "dyna_substitution_matrix": (C.c_int, [C.c_char_p, _i8p]),
     "dyna_aa_index_table": (None, [_i8p]),
     "dyna_nw_pair_stats": (C.c_int, [_u8p, _i64p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _u32p]),

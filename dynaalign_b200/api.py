@@ -24,7 +24,7 @@ from ._lib import DynaAlignError, check, flatten, lib, ptr
 __all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
            "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
            "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
-           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "DynaAlignError"]
+           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError"]
 
 
 def dimnames(n):
@@ -345,6 +345,43 @@ def compute_distance_matrix(sig_matrix):
     out = np.zeros((n_docs, n_docs), dtype=np.float64, order="F")
     check(lib().dyna_mh_match_matrix(ptr(codes, C.c_uint32), n_docs, n_hash, L.MH_DISTANCE, ptr(out, C.c_double), 1))
     return out
+
+
+def vocab_ranks(sequences, k):
+    """create_vocab + the vocabulary rank of every shingle, on the device (no dense V x N matrix).
+    Returns (vocabulary list[str], ranks int32[], offsets int64[n+1])."""
+    sequences = list(sequences)
+    res, off = flatten(sequences)
+    n = len(sequences)
+    total = int(sum(max(len(s) - k + 1, 0) for s in sequences))
+    ranks = np.zeros(max(total, 1), dtype=np.int32)
+    roff = np.zeros(n + 1, dtype=np.int64)
+    keys = np.zeros(max(total, 1), dtype=np.uint64)
+    V = C.c_int64(0)
+    check(lib().dyna_minhash_vocab_ranks(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, int(k), ptr(keys, C.c_uint64), len(keys),
+                                         C.byref(V), ptr(ranks, C.c_int32), ptr(roff, C.c_int64)))
+    vocab = [int(x).to_bytes(8, "big")[8 - k:].decode("latin-1") for x in keys[:V.value]]
+    return vocab, ranks[:total], roff
+
+
+def minhash_gpu(sequences, k, n_hash, rng=None, hash_params=None):
+    """minhash() with the whole pipeline on the device: vocabulary by sort/unique, signatures from rank lists, distance by
+    the match kernel.  Same list as minhash() except that char_matrix is not materialised (ranks/offsets instead)."""
+    sequences = list(sequences)
+    vocab, ranks, roff = vocab_ranks(sequences, k)
+    max_val = len(vocab)
+    if hash_params is None:
+        hash_params = create_hash_parameters(n_hash, max_val, rng)
+    a = np.ascontiguousarray(hash_params["a"], dtype=np.int64)
+    b = np.ascontiguousarray(hash_params["b"], dtype=np.int64)
+    n = len(sequences)
+    sig = np.zeros((n, len(a)), dtype=np.uint32)
+    rk = ranks if ranks.size else np.ones(1, dtype=np.int32)
+    check(lib().dyna_mh_signatures_linear(ptr(rk, C.c_int32), ptr(roff, C.c_int64), n, ptr(a, C.c_int64), ptr(b, C.c_int64),
+                                          int(max_val), len(a), ptr(sig, C.c_uint32)))
+    dist = np.zeros((n, n), dtype=np.float64, order="F")
+    check(lib().dyna_mh_match_matrix(ptr(sig, C.c_uint32), n, len(a), L.MH_DISTANCE, ptr(dist, C.c_double), 1))
+    return {"vocabulary": vocab, "ranks": ranks, "rank_offsets": roff, "sig_matrix": sig.T.astype(np.float64), "dist_matrix": dist}
 
 
 def minhash(sequences, k, n_hash, rng=None, hash_params=None):

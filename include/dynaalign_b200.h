@@ -103,6 +103,15 @@ DYNA_API int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets, 
 DYNA_API int dyna_mh_signatures_linear(const int32_t* ranks, const int64_t* rank_offsets, int64_t n, const int64_t* a,
                               const int64_t* b, int64_t m, int n_hash, uint32_t* sig_out);
 
+/* Device front end of the R pipeline: create_vocab (R/minHash.R:38-41) and, instead of the dense V x N characteristic
+ * matrix of create_char_matrix (:60-66), the 1-based vocabulary rank of every k-shingle in document order
+ * (ranks_out[rank_offsets_out[d] .. rank_offsets_out[d+1]) for document d) -- exactly the input of
+ * dyna_mh_signatures_linear.  Vocabulary entries are the k bytes packed big-endian into a uint64 (sorted ascending ==
+ * byte-wise string order).  k <= 8.  Any sequence shorter than k raises shingle()'s error text (:15-16).
+ * vocab_keys_out may be NULL; ranks_out must hold sum(len_d - k + 1) entries, rank_offsets_out n+1. */
+DYNA_API int dyna_minhash_vocab_ranks(const uint8_t* residues, const int64_t* offsets, int64_t n, int k, uint64_t* vocab_keys_out,
+                             int64_t vocab_capacity, int64_t* vocab_size_out, int32_t* ranks_out, int64_t* rank_offsets_out);
+
 /* ---------------------------------------------------------------- Needleman-Wunsch (src/pairwiseSeqAlign.cpp) */
 DYNA_API int dyna_substitution_matrix(const char* name, int8_t* out576); /* 24x24 row-major; unknown name -> reference error */
 DYNA_API void dyna_aa_index_table(int8_t* out256);                       /* byte -> 0..23, -1 = not in the alphabet */

@@ -205,3 +205,22 @@ def test_plan_subsets_reuse_signatures(evp):
         sub.close()
     assert (plan.signatures() == port.mh_signatures(evp, 2, port.hashfamily_seeds(42, 50))).all()
     plan.close()
+
+
+def test_device_vocabulary_and_full_gpu_minhash(evp):
+    # create_vocab / ranks on the device == the R restatement; full pipeline == R restatement given the same (a, b)
+    for seqs, k in [(evp[:200], 3), (["ACDEGHHIKLLL", "ACDEGHHIKLMN", "XXXXXYYYYYYZZ"], 3), (evp, 1), (evp[:50], 8)]:
+        vocab, ranks, roff = da.vocab_ranks(seqs, k)
+        assert vocab == R.create_vocab(seqs, k)
+        wr, wo = R.shingle_ranks(seqs, vocab, k)
+        assert (ranks == wr).all() and (roff == wo).all()
+    seqs = evp[:120]
+    vocab = R.create_vocab(seqs, 4)
+    hp = R.create_hash_parameters(200, len(vocab), np.random.default_rng(8))
+    want = R.minhash(seqs, 4, 200, hash_params=hp)
+    got = da.minhash_gpu(seqs, 4, 200, hash_params=hp)
+    assert got["vocabulary"] == want["vocabulary"]
+    assert (got["sig_matrix"] == want["sig_matrix"]).all()
+    assert same_matrix(got["dist_matrix"], want["dist_matrix"])
+    with pytest.raises(da.DynaAlignError, match="'k' must be a positive integer between 1 and 2"):
+        da.vocab_ranks(["ACDE", "AC", "ACDEF"], 3)
