@@ -707,6 +707,7 @@ int launch_warp2_R(int var, const NwDeviceData& d, const NwUnit* d_units, int nu
   if (const char* e = getenv("DYNA_NW2_INPLACE_MINR")) inplace_min_r = atoi(e);
   if (var == 0 && R >= 10 && R <= 12) nw_warp2_kernel<(R >= 10 && R <= 12) ? R : 10, 0, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
   else if (R >= inplace_min_r) nw_warp2_kernel<R, 1, true, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);  // tall strips: 4-warp CTAs, 3 per SM
+  else if (getenv("DYNA_NW2_THREADS128")) nw_warp2_kernel<R, 1, false, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);
   else nw_warp2_kernel<R, 1, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;

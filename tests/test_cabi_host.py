@@ -134,3 +134,14 @@ def test_quantile_type7_from_histogram_matches_r_definition():
                 assert ((counts >= mc) == kept).all()
     with pytest.raises(da.DynaAlignError):
         da.quantile_type7_counts(np.zeros(5, np.uint64), 4, 0.5)
+
+
+def test_vocab_argument_errors_before_device():
+    import ctypes as C2
+    from dynaalign_b200._lib import flatten, lib, ptr
+    res, off = flatten(["ACDE", "AC", "ACDEF"])
+    V = C2.c_int64(0)
+    rc = lib().dyna_minhash_vocab_ranks(ptr(res, C2.c_uint8), ptr(off, C2.c_int64), 3, 3, None, 0, C2.byref(V), None, None)
+    assert rc == _lib.ERR_INVALID and _lib.last_error() == "'k' must be a positive integer between 1 and 2"
+    rc = lib().dyna_minhash_vocab_ranks(ptr(res, C2.c_uint8), ptr(off, C2.c_int64), 3, 0, None, 0, C2.byref(V), None, None)
+    assert rc == _lib.ERR_INVALID and _lib.last_error() == "'k' must be a positive integer between 1 and 4"
