@@ -528,10 +528,10 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     const int m = (int)(offsets[i + 1] - offsets[i]);
     int kind, R, step;
     if (m == 0) { kind = 0; R = 0; step = 4096; }
-    else if (getenv("DYNA_NW_FORCE_WARP2") && fits16(m)) { kind = 4; R = std::max(2, nw_warp_R(m)); step = 2 * kNwWarpUnitPairs; }
+    else if (getenv("DYNA_NW_FORCE_WARP2") && fits16(m) && max_len <= kNwWarp2MaxCols) { kind = 4; R = std::max(2, nw_warp_R(m)); step = 2 * kNwWarpUnitPairs; }
     else if (nw_use_thread_kernel(m) && fits16(m)) { kind = 5; R = nw_thread_R(m); step = 2 * kNwThreadUnitPairs; }
     else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
-    else if (fits16(m)) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
+    else if (fits16(m) && max_len <= kNwWarp2MaxCols) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
     else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
     else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
     NwClass* c = get_class(kind, R);

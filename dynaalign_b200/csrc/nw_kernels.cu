@@ -366,13 +366,21 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
 // INPLACE: one register set for (H, S) instead of the ping-pong pair -- 4R instead of 7R state registers at the price
 // of three register moves per row (they issue as IMAD.MOV, off the ALU pipe).  Used for tall strips (R >= 13), where
 // the ping-pong version drops to one CTA per SM.
+// Per-step overhead matters (an 11-row strip is only ~150 instructions per step), so the step loop avoids ALU-pipe work
+// that is not the recurrence: both column sequences are staged per warp in shared memory (the shorter one padded with
+// class 24, so no bounds test and no 64-bit address arithmetic per step), the active test is one unsigned compare, and
+// the border row reaches lane 0 through a ROTATING shuffle from lane 31, which holds the border constants whenever the
+// strip layout leaves it idle (m <= 31*R) -- no per-step select for lane 0.
+constexpr int kNwStageCols = 1024;  // column-sequence length limit of the packed warp kernel (host-checked)
+
 template <int R, int VAR, bool INPLACE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   using S = Strip<R>;
-  __shared__ uint32_t prof[25 * 32 * S::RWS];  // class 24 = padding residue, all-zero entries
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int nwarps = THREADS / 32;
+  __shared__ uint32_t prof[25 * 32 * S::RWS];  // class 24 = padding residue, all-zero entries
+  __shared__ uint8_t stage[nwarps][2][kNwStageCols + 8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int go = d.gap_open, ge = d.gap_ext;
   const uint32_t ngo2 = pack16(-go);
   const uint32_t sent2 = pack16(kSentinel16);
@@ -381,6 +389,9 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   c.one = d.one;
   c.zero = d.one - 1u;
   const unsigned full = 0xFFFFFFFFu;
+  const int src_lane = (lane + 31) & 31;  // rotating "shuffle up": lane 0 reads lane 31
+  uint8_t* sA = stage[warp][0];
+  uint8_t* sB = stage[warp][1];
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
     const NwUnit un = units[u];
@@ -393,7 +404,9 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int lm = (m - 1) / R;
     const int km = (m - 1) - lm * R;
     const int r0 = lane * R;
+    const bool rot = (lm < 31);  // lane 31 idle: it can hold the border row for lane 0
     const int npairs2 = (un.j_count + 1) >> 1;
+    const uint32_t* plane = prof + lane * S::RWS;
 
     for (int pp = warp; pp < npairs2; pp += nwarps) {
       int jA = un.j_begin + 2 * pp;
@@ -405,8 +418,16 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
         int tj = jA; jA = jB; jB = tj;
         int tn = nA; nA = nB; nB = tn;
       }
-      const uint8_t* __restrict__ bA = d.codes + d.off[jA];
-      const uint8_t* __restrict__ bB = d.codes + d.off[jB];
+      {  // stage both column sequences (B padded with the zero-profile class up to nA)
+        const uint8_t* __restrict__ bA = d.codes + d.off[jA];
+        const uint8_t* __restrict__ bB = d.codes + d.off[jB];
+        __syncwarp();
+        for (int q = lane; q < nA; q += 32) {
+          sA[q] = bA[q];
+          sB[q] = (q < nB) ? bB[q] : (uint8_t)24;
+        }
+        __syncwarp();
+      }
 
       constexpr int R2 = INPLACE ? 1 : R;  // second register set only for the ping-pong version
       uint32_t H0[R], H1[R2], El[R], SA0[R], SA1[R2], SB0[R], SB1[R2];
@@ -422,30 +443,34 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       }
       uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
       uint32_t prevUpSA = 0u, prevUpSB = 0u;
-      uint32_t outH = 0u, outF = 0u, outSA = 0u, outSB = 0u;
+      // lane 31 (idle when rot) carries the border row: H_diag = -go+ge (slanted), F = sentinel, stats 0
+      uint32_t outH = bord2, outF = sent2, outSA = 0u, outSB = 0u;
       uint32_t resB = 0u;
+      const unsigned n_act = (lane <= lm) ? (unsigned)nA : 0u;  // columns this lane processes
+      const int capB = (lane == lm) ? nB - 1 : -1;              // column at which pair B's result is final
       const int T = nA + lm;
       for (int t0 = 0; t0 < T; t0 += 2) {
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
-          const int t = t0 + ph;
-          const int jc = t - lane;
-          uint32_t rH = __shfl_up_sync(full, outH, 1);
-          uint32_t rF = __shfl_up_sync(full, outF, 1);
-          uint32_t rSA = __shfl_up_sync(full, outSA, 1);
-          uint32_t rSB = __shfl_up_sync(full, outSB, 1);
-          if (lane == 0) {  // border row
-            rH = bord2;
-            rF = sent2;
-            rSA = 0u;
-            rSB = 0u;
+          const int jc = t0 + ph - lane;
+          uint32_t rH = __shfl_sync(full, outH, src_lane);
+          uint32_t rF = __shfl_sync(full, outF, src_lane);
+          uint32_t rSA = __shfl_sync(full, outSA, src_lane);
+          uint32_t rSB = __shfl_sync(full, outSB, src_lane);
+          if (!rot) {  // all 32 lanes own rows: lane 0 takes the border row explicitly
+            if (lane == 0) {
+              rH = bord2;
+              rF = sent2;
+              rSA = 0u;
+              rSB = 0u;
+            }
           }
-          if (jc >= 0 && jc < nA && lane <= lm) {
-            const int cA = bA[jc];
-            const int cB = (jc < nB) ? (int)bB[jc] : 24;
+          if ((unsigned)jc < n_act) {
+            const int cA = sA[jc];
+            const int cB = sB[jc];
             uint32_t pwA[S::RW], pwB[S::RW];
-            const uint32_t* pa = prof + cA * (32 * S::RWS) + lane * S::RWS;
-            const uint32_t* pb = prof + cB * (32 * S::RWS) + lane * S::RWS;
+            const uint32_t* pa = plane + cA * (32 * S::RWS);
+            const uint32_t* pb = plane + cB * (32 * S::RWS);
 #pragma unroll
             for (int w = 0; w < S::RW; ++w) {
               pwA[w] = pa[w];
@@ -473,7 +498,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
             prevUpH = rH;
             prevUpSA = rSA;
             prevUpSB = rSB;
-            if (lane == lm && jc == nB - 1) {  // the shorter sequence ends here: capture its result
+            if (jc == capB) {  // the shorter sequence ends here: capture its result
 #pragma unroll
               for (int k = 0; k < R; ++k)
                 if (k == km) resB = (!INPLACE && ph == 0) ? SB1[INPLACE ? 0 : k] : SB0[k];
@@ -701,13 +726,9 @@ int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int 
 }
 
 template <int R>
-int launch_warp2_R(int var, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
-  // variant 0 (A/B measurements) is only instantiated for the strip heights of the benchmark proteins
-  int inplace_min_r = 13;
-  if (const char* e = getenv("DYNA_NW2_INPLACE_MINR")) inplace_min_r = atoi(e);
-  if (var == 0 && R >= 10 && R <= 12) nw_warp2_kernel<(R >= 10 && R <= 12) ? R : 10, 0, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
-  else if (R >= inplace_min_r) nw_warp2_kernel<R, 1, true, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);  // tall strips: 4-warp CTAs, 3 per SM
-  else if (getenv("DYNA_NW2_THREADS128")) nw_warp2_kernel<R, 1, false, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);
+int launch_warp2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  // short strips: ping-pong register sets, 8-warp CTAs; tall strips (R >= 13): one register set, 4-warp CTAs (3 per SM)
+  if constexpr (R >= 13) nw_warp2_kernel<R, 1, true, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);
   else nw_warp2_kernel<R, 1, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
@@ -788,12 +809,10 @@ int launch_nw_thread2(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 
 int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   if (num_units == 0) return DYNA_OK;
-  int var = 1;
-  if (const char* e = getenv("DYNA_NW2_VARIANT")) var = atoi(e);
   switch (R) {
 #define DYNA_CASE(RR) \
   case RR:            \
-    return launch_warp2_R<RR>(var, d, d_units, num_units, st);
+    return launch_warp2_R<RR>(d, d_units, num_units, st);
     DYNA_CASE(2) DYNA_CASE(3) DYNA_CASE(4) DYNA_CASE(5) DYNA_CASE(6) DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9)
     DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12) DYNA_CASE(13) DYNA_CASE(14) DYNA_CASE(15) DYNA_CASE(16) DYNA_CASE(17)
     DYNA_CASE(18) DYNA_CASE(19) DYNA_CASE(20)

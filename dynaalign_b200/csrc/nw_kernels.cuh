@@ -26,6 +26,7 @@ struct NwDeviceData {
 
 constexpr int kNwThreadMaxRows = 32;  // rows handled by the thread-per-pair kernel
 constexpr int kNwWarpMaxR = 24;       // rows per lane of the warp-per-pair kernel (32*24 = 768 rows per pass)
+constexpr int kNwWarp2MaxCols = 1024;  // column-sequence length limit of the packed warp kernel (shared-memory staging)
 constexpr int kNwWarp2MaxR = 20;      // strip height limit of the two-pairs-per-warp 16-bit kernel (register budget)
 constexpr int kNwWarpUnitPairs = 32;  // pairs per unit (8 warps x 4)
 constexpr int kNwThreadUnitPairs = 512;
