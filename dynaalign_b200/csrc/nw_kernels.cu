@@ -114,12 +114,12 @@ __device__ __forceinline__ void strip_column(const int (&Ho)[R], const uint32_t 
 }
 
 // profile of rows [row0, row0 + LANES*R) of the row sequence (length m) into shared memory, strip-major per class
-template <int R, int LANES>
+template <int R, int LANES, int STRIDE_WORDS = Strip<R>::RWS>
 __device__ __forceinline__ void build_profile(uint32_t* prof, const uint8_t* __restrict__ a, int m, int row0,
                                               const int8_t* __restrict__ sub, int bias, int tid, int nthreads) {
   using S = Strip<R>;
   uint16_t* p16 = reinterpret_cast<uint16_t*>(prof);
-  constexpr int per_class = LANES * S::RWS * 2;  // 16-bit entries per residue class (incl. padding)
+  constexpr int per_class = LANES * STRIDE_WORDS * 2;  // 16-bit entries per residue class (incl. padding)
   for (int idx = tid; idx < 24 * LANES * S::RP; idx += nthreads) {
     const int c = idx / (LANES * S::RP);
     const int rem = idx - c * (LANES * S::RP);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void build_profile(uint32_t* prof, const uint8_t* __r
       const int ar = a[r];
       e = (uint16_t)((uint8_t)(sub[ar * 24 + c] + bias)) | (uint16_t)((ar == c) ? 0x0100 : 0);
     }
-    p16[c * per_class + lane * (S::RWS * 2) + k] = e;
+    p16[c * per_class + lane * (STRIDE_WORDS * 2) + k] = e;
   }
 }
 
@@ -327,13 +327,27 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
                                               uint32_t (&SBn)[R], const uint32_t (&pwA)[Strip<R>::RW],
                                               const uint32_t (&pwB)[Strip<R>::RW], uint32_t diagH, uint32_t dSA,
                                               uint32_t dSB, uint32_t F, uint32_t upSA, uint32_t upSB, uint32_t ngo2,
-                                              const Stat2Consts& c, uint32_t& outF) {
+                                              const Stat2Consts& c, uint32_t& outF, const uint4* __restrict__ incA4 = nullptr,
+                                              const uint4* __restrict__ incB4 = nullptr) {
+  // VAR 2: the stat increments (1 | eq << 16) are read ready-made from a shared-memory table, four rows per 128-bit
+  // load, instead of being permuted out of the profile word: two fewer ALU-pipe instructions per two cells
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     const uint32_t wA = pwA[k >> 1], wB = pwB[k >> 1];
     const uint32_t sP = (k & 1) ? prmt<0xE6A2>(wA, wB) : prmt<0xC480>(wA, wB);  // [sext16(sA) | sext16(sB) << 16]
-    const uint32_t incA = (k & 1) ? prmt<0x5354>(wA, c.one) : prmt<0x5154>(wA, c.one);  // 1 | eq << 16
-    const uint32_t incB = (k & 1) ? prmt<0x5354>(wB, c.one) : prmt<0x5154>(wB, c.one);
+    uint32_t incA, incB;
+    if (VAR == 2) {
+      if ((k & 3) == 0) {
+        qa = incA4[k >> 2];
+        qb = incB4[k >> 2];
+      }
+      incA = (k & 3) == 0 ? qa.x : (k & 3) == 1 ? qa.y : (k & 3) == 2 ? qa.z : qa.w;
+      incB = (k & 3) == 0 ? qb.x : (k & 3) == 1 ? qb.y : (k & 3) == 2 ? qb.z : qb.w;
+    } else {
+      incA = (k & 1) ? prmt<0x5354>(wA, c.one) : prmt<0x5154>(wA, c.one);  // 1 | eq << 16
+      incB = (k & 1) ? prmt<0x5354>(wB, c.one) : prmt<0x5154>(wB, c.one);
+    }
     const uint32_t E = El[k];
     const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
     bool puB, puA, pdB, pdA;
@@ -371,15 +385,49 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
 // class 24, so no bounds test and no 64-bit address arithmetic per step), the active test is one unsigned compare, and
 // the border row reaches lane 0 through a ROTATING shuffle from lane 31, which holds the border constants whenever the
 // strip layout leaves it idle (m <= 31*R) -- no per-step select for lane 0.
-constexpr int kNwStageCols = 1024;  // column-sequence length limit of the packed warp kernel (host-checked)
+constexpr int kNwStageCols = 1024;
+
+// dynamic shared memory layout of nw_warp2_kernel
+template <int R, int VAR, int THREADS>
+struct Warp2Smem {
+  // increment-table stride per lane strip: a multiple of 4 words (128-bit loads) and an ODD multiple (conflict-free
+  // across the 8 lanes of a quarter warp): 4, 12 or 20
+  static constexpr int kIncStride = R <= 4 ? 4 : (R <= 12 ? 12 : 20);
+  // score-profile stride per lane strip (odd word count: conflict-free 32-bit loads).  A 128-bit-load layout of the
+  // score profile was measured slower (2.76 vs 2.94 TCUPS) and is not kept.
+  static constexpr int kProfStride = Strip<R>::RWS;
+  static constexpr int kProfBytes = 25 * 32 * kProfStride * 4;
+  static constexpr int kIncBytes = VAR == 2 ? 25 * 32 * kIncStride * 4 : 0;
+  static constexpr int kStageBytes = (THREADS / 32) * 2 * (kNwStageCols + 8);
+  static constexpr int kIncOff = 0;                                  // 16-byte aligned first
+  static constexpr int kProfOff = kIncOff + kIncBytes;
+  static constexpr int kStageOff = kProfOff + kProfBytes;
+  static constexpr int kTotal = kStageOff + kStageBytes;
+};  // column-sequence length limit of the packed warp kernel (host-checked)
 
 template <int R, int VAR, bool INPLACE, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 2 : 3)
 nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   using S = Strip<R>;
+  using L = Warp2Smem<R, VAR, THREADS>;
   constexpr int nwarps = THREADS / 32;
-  __shared__ uint32_t prof[25 * 32 * S::RWS];  // class 24 = padding residue, all-zero entries
-  __shared__ uint8_t stage[nwarps][2][kNwStageCols + 8];
+  // VAR 2 needs ~77 KB (dynamic shared memory); the other variants stay within the 48 KB static limit, which also
+  // gives the compiler constant shared addresses (measured 2.5 % faster than the dynamic form)
+  uint32_t* prof;        // score profile, class 24 = padding residue (all-zero entries)
+  uint32_t* incT;        // VAR 2: [class][lane][kIncStride] stat increments
+  uint8_t* stage_base;   // per-warp staged column sequences
+  if constexpr (VAR == 2) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    prof = reinterpret_cast<uint32_t*>(smem_dyn + L::kProfOff);
+    incT = reinterpret_cast<uint32_t*>(smem_dyn + L::kIncOff);
+    stage_base = smem_dyn + L::kStageOff;
+  } else {
+    __shared__ uint32_t prof_s[25 * 32 * L::kProfStride];
+    __shared__ uint8_t stage_s[L::kStageBytes];
+    prof = prof_s;
+    incT = prof_s;
+    stage_base = stage_s;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int go = d.gap_open, ge = d.gap_ext;
   const uint32_t ngo2 = pack16(-go);
@@ -390,23 +438,34 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   c.zero = d.one - 1u;
   const unsigned full = 0xFFFFFFFFu;
   const int src_lane = (lane + 31) & 31;  // rotating "shuffle up": lane 0 reads lane 31
-  uint8_t* sA = stage[warp][0];
-  uint8_t* sB = stage[warp][1];
+  uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwStageCols + 8);
+  uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwStageCols + 8);
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
     const NwUnit un = units[u];
     const int row = un.row;
     const int m = d.off[row + 1] - d.off[row];
     __syncthreads();
-    build_profile<R, 32>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
-    for (int idx = tid; idx < 32 * S::RWS; idx += THREADS) prof[24 * 32 * S::RWS + idx] = 0u;
+    build_profile<R, 32, L::kProfStride>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
+    for (int idx = tid; idx < 32 * L::kProfStride; idx += THREADS) prof[24 * 32 * L::kProfStride + idx] = 0u;
+    if (VAR == 2) {  // increment table: 1 | (row residue == class) << 16; padding rows and class 24 count steps only
+      const uint8_t* __restrict__ a = d.codes + d.off[row];
+      for (int idx = tid; idx < 25 * 32 * L::kIncStride; idx += THREADS) {
+        const int cls = idx / (32 * L::kIncStride);
+        const int rem = idx - cls * (32 * L::kIncStride);
+        const int ln = rem / L::kIncStride, k = rem - ln * L::kIncStride;
+        const int r = ln * R + k;
+        incT[idx] = 1u | ((k < R && r < m && cls < 24 && a[r] == cls) ? 0x10000u : 0u);
+      }
+    }
     __syncthreads();
     const int lm = (m - 1) / R;
     const int km = (m - 1) - lm * R;
     const int r0 = lane * R;
     const bool rot = (lm < 31);  // lane 31 idle: it can hold the border row for lane 0
     const int npairs2 = (un.j_count + 1) >> 1;
-    const uint32_t* plane = prof + lane * S::RWS;
+    const uint32_t* plane = prof + lane * L::kProfStride;
+    const uint32_t* ilane = incT + lane * L::kIncStride;
 
     for (int pp = warp; pp < npairs2; pp += nwarps) {
       int jA = un.j_begin + 2 * pp;
@@ -469,8 +528,10 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
             const int cA = sA[jc];
             const int cB = sB[jc];
             uint32_t pwA[S::RW], pwB[S::RW];
-            const uint32_t* pa = plane + cA * (32 * S::RWS);
-            const uint32_t* pb = plane + cB * (32 * S::RWS);
+            const uint32_t* pa = plane + cA * (32 * L::kProfStride);
+            const uint32_t* pb = plane + cB * (32 * L::kProfStride);
+            const uint4* ia = reinterpret_cast<const uint4*>(ilane + cA * (32 * L::kIncStride));
+            const uint4* ib = reinterpret_cast<const uint4*>(ilane + cB * (32 * L::kIncStride));
 #pragma unroll
             for (int w = 0; w < S::RW; ++w) {
               pwA[w] = pa[w];
@@ -478,19 +539,19 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
             }
             if constexpr (INPLACE) {
               strip_column2<R, VAR>(H0, H0, El, SA0, SA0, SB0, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
-                                    ngo2, c, outF);
+                                    ngo2, c, outF, ia, ib);
               outH = H0[R - 1];
               outSA = SA0[R - 1];
               outSB = SB0[R - 1];
             } else if (ph == 0) {
               strip_column2<R, VAR>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
-                                    ngo2, c, outF);
+                                    ngo2, c, outF, ia, ib);
               outH = H1[R - 1];
               outSA = SA1[R - 1];
               outSB = SB1[R - 1];
             } else {
               strip_column2<R, VAR>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
-                                    ngo2, c, outF);
+                                    ngo2, c, outF, ia, ib);
               outH = H0[R - 1];
               outSA = SA0[R - 1];
               outSB = SB0[R - 1];
@@ -725,13 +786,31 @@ int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int 
   return DYNA_OK;
 }
 
-template <int R>
-int launch_warp2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
-  // short strips: ping-pong register sets, 8-warp CTAs; tall strips (R >= 13): one register set, 4-warp CTAs (3 per SM)
-  if constexpr (R >= 13) nw_warp2_kernel<R, 1, true, 128><<<num_units, 128, 0, st>>>(d, d_units, num_units);
-  else nw_warp2_kernel<R, 1, false, kWarpThreads><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units);
+template <int R, int VAR, bool INPLACE, int THREADS>
+int launch_warp2_inst(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  using L = Warp2Smem<R, VAR, THREADS>;
+  if constexpr (VAR == 2) {
+    DYNA_CUDA(cudaFuncSetAttribute(nw_warp2_kernel<R, VAR, INPLACE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    nw_warp2_kernel<R, VAR, INPLACE, THREADS><<<num_units, THREADS, L::kTotal, st>>>(d, d_units, num_units);
+  } else {
+    nw_warp2_kernel<R, VAR, INPLACE, THREADS><<<num_units, THREADS, 0, st>>>(d, d_units, num_units);
+  }
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
+}
+
+template <int R>
+int launch_warp2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  // measured on B200 (TCUPS, config 5 / config 2):
+  //   strips R <= 12: ping-pong register sets, 8-warp CTAs, increments from the shared-memory table (VAR 2): 2.94
+  //                   (VAR 1, increments by PRMT: 2.72 on the same box; one register set: 2.58)
+  //   strips R >= 13: one register set, 4-warp CTAs, increments by PRMT (VAR 1): 2.60 (VAR 2: 2.48; ping-pong: 2.27)
+  if constexpr (R >= 13) return launch_warp2_inst<R, 1, true, 128>(d, d_units, num_units, st);
+  else {
+    const int var = getenv("DYNA_NW2_VARIANT") ? atoi(getenv("DYNA_NW2_VARIANT")) : 2;
+    if (var == 1) return launch_warp2_inst<R, 1, false, kWarpThreads>(d, d_units, num_units, st);
+    return launch_warp2_inst<R, 2, false, kWarpThreads>(d, d_units, num_units, st);
+  }
 }
 
 int launch_warp_multipass(bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, int32_t* d_scratch,
