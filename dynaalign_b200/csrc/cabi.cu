@@ -4,6 +4,7 @@
 // There is no CPU compute path in this file: every similarity value is produced by the kernels in
 // mh_kernels.cu / nw_kernels.cu, and a missing or failing CUDA device is an error.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -31,6 +32,7 @@ int use_device(int device) {
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   if (device < 0 || device >= count) return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: device %d out of range (0..%d)", device, count - 1);
   DYNA_CUDA(cudaSetDevice(device));
+  dev_pool_keep_cached(device);
   return DYNA_OK;
 }
 
@@ -205,6 +207,11 @@ extern "C" dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_
   if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch) || p->counts.alloc((size_t)p->pairs))
     return nullptr;
   if (mh_plan_setup16(p.get()) != DYNA_OK) return nullptr;
+  // allocations are stream-ordered on the legacy default stream: make them visible to any stream the caller uses
+  if (cudaStreamSynchronize(0) != cudaSuccess) {
+    fail(DYNA_ERR_CUDA, "DynaAlign CUDA: plan allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
   return p.release();
 }
 
@@ -868,17 +875,36 @@ extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets
 // =====================================================================================================
 // NW host entry points
 // =====================================================================================================
+namespace {
+struct PhaseTimer {  // DYNA_TIMING=1: per-phase wall clock of the host entry points on stderr
+  bool on = getenv("DYNA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dyna timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 extern "C" int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
                                   int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint32_t* matches_out,
                                   uint32_t* length_out) {
+  PhaseTimer tm;
   dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, g_device);
+  tm.lap("nw plan create");
   if (!p) return err_slot().find("CUDA") != std::string::npos ? DYNA_ERR_CUDA
                  : (err_slot().find("not supported") != std::string::npos || err_slot().find("exceed") != std::string::npos)
                      ? DYNA_ERR_UNSUPPORTED
                      : DYNA_ERR_INVALID;
   int rc = dyna_nw_plan_run(p, nullptr);
+  if (tm.on) cudaDeviceSynchronize();
+  tm.lap("nw kernels");
   if (rc == DYNA_OK) rc = dyna_nw_plan_fetch(p, matches_out, length_out, nullptr);
+  tm.lap("nw fetch (D2H)");
   dyna_nw_plan_destroy(p);
+  tm.lap("nw plan destroy");
   return rc;
 }
 

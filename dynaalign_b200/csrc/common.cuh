@@ -42,7 +42,22 @@ inline int fail(int code, const char* fmt, ...) {
     if (rc__ != DYNA_OK) return rc__; \
   } while (0)
 
-// RAII device buffer (cudaMalloc/cudaFree on the current device)
+// Device memory comes from the stream-ordered allocator with the pool's release threshold lifted, so the buffers of
+// one call are recycled by the next (clusterbreak invokes sim_fn once per recursion node; plain cudaMalloc/cudaFree of
+// the multi-GB result buffers was measured at up to 1 s per call).  All allocation and release is ordered on the
+// legacy default stream.
+inline void dev_pool_keep_cached(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done[device] = true;
+}
+
+// RAII device buffer on the current device
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -55,11 +70,11 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) count = 1;
-    DYNA_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    DYNA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), 0));
     return DYNA_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, 0);
     p = nullptr;
     n = 0;
   }

@@ -131,7 +131,9 @@ DYNA_API int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets, 
  * A plan owns device buffers on one GPU for one row range.  `run` only enqueues kernels on `stream`
  * (a cudaStream_t passed as void*, NULL = default stream) so callers can time it with their own events;
  * `fetch` copies results to host memory (synchronous on `stream`).  Used by bench.py for the
- * inputs-resident-in-HBM figure and by the host entry points above. */
+ * inputs-resident-in-HBM figure and by the host entry points above.  Device memory comes from the stream-ordered
+ * allocator on the legacy default stream and stays cached in the pool between calls; work enqueued on a non-blocking
+ * stream must have completed before the plan is destroyed. */
 typedef struct dyna_mh_plan dyna_mh_plan;
 DYNA_API dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_begin, int64_t row_end, int device);
 DYNA_API int dyna_mh_plan_upload_sequences(dyna_mh_plan*, const uint8_t* residues, const int64_t* offsets, int k,
