@@ -53,6 +53,7 @@ _SIGS = {
     "dyna_mh_plan_upload_signatures": (C.c_int, [C.c_void_p, _u32p, C.c_void_p]),
     "dyna_mh_plan_run_signatures": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dyna_mh_plan_run_match": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dyna_mh_plan_run_match_fetch": (C.c_int, [C.c_void_p, _u16p, C.c_void_p]),
     "dyna_mh_plan_fetch_signatures": (C.c_int, [C.c_void_p, _u32p, C.c_void_p]),
     "dyna_mh_plan_fetch_counts": (C.c_int, [C.c_void_p, _u16p, C.c_void_p]),
     "dyna_mh_plan_create_subset": (C.c_void_p, [C.c_void_p, _i64p, C.c_int64, C.c_int64, C.c_int64]),

@@ -224,9 +224,12 @@ class MinHashPlan:
         return out
 
     def match_counts(self):
-        self._match()
         out = np.zeros(max(tri_strict_size(self.n), 1), dtype=np.uint16)
-        check(lib().dyna_mh_plan_fetch_counts(self._h, ptr(out, C.c_uint16), None))
+        if self._matched:
+            check(lib().dyna_mh_plan_fetch_counts(self._h, ptr(out, C.c_uint16), None))
+        else:  # match and copy back chunk by chunk, overlapped
+            check(lib().dyna_mh_plan_run_match_fetch(self._h, ptr(out, C.c_uint16), None))
+            self._matched = True
         return out[:tri_strict_size(self.n)]
 
     def histogram(self):

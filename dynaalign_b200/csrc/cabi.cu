@@ -406,6 +406,57 @@ extern "C" int dyna_mh_plan_threshold_edges(dyna_mh_plan* p, int min_count, int6
   return DYNA_OK;
 }
 
+// match + fetch with the device-to-host copy of finished row chunks overlapped with the matching of the next ones:
+// the counts slab of a row range is contiguous, so the plan's range is cut into pair-balanced chunks, each matched on
+// `stream` and copied on a second stream as soon as its kernel has finished.  counts_out should be pinned memory.
+extern "C" int dyna_mh_plan_run_match_fetch(dyna_mh_plan* p, uint16_t* counts_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (!p->have_sigT) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match_fetch: no signatures on the device");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = p->row_end - p->row_begin;
+  if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
+  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, p->pairs / (64ll << 20)));
+  // pair-balanced chunk boundaries inside [row_begin, row_end)
+  std::vector<int64_t> b((size_t)nchunks + 1);
+  b[0] = p->row_begin;
+  const int64_t base = tri_strict_rows(p->n, p->row_begin);
+  int64_t r = p->row_begin;
+  for (int c = 1; c < nchunks; ++c) {
+    const int64_t target = base + p->pairs * c / nchunks;
+    while (r < p->row_end && tri_strict_rows(p->n, r) < target) ++r;
+    b[(size_t)c] = r;
+  }
+  b[(size_t)nchunks] = p->row_end;
+  cudaStream_t copy_st;
+  DYNA_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+  std::vector<cudaEvent_t> ev((size_t)nchunks);
+  int rc = DYNA_OK, launches = 0;
+  for (int c = 0; c < nchunks && rc == DYNA_OK; ++c) {
+    cudaEventCreateWithFlags(&ev[(size_t)c], cudaEventDisableTiming);
+    const int64_t r0 = b[(size_t)c], r1 = b[(size_t)c + 1];
+    if (r1 <= r0) continue;
+    const int64_t off = tri_strict_rows(p->n, r0) - base, cnt = tri_strict_rows(p->n, r1) - tri_strict_rows(p->n, r0);
+    int l = 0;
+    rc = launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, r0, r1, p->counts.p + off,
+                         p->use16 ? p->sigP.p : nullptr, p->use16 ? p->overflow.p : nullptr, st, &l);
+    launches += l;
+    if (rc != DYNA_OK) break;
+    cudaEventRecord(ev[(size_t)c], st);
+    cudaStreamWaitEvent(copy_st, ev[(size_t)c], 0);
+    if (cnt > 0 && cudaMemcpyAsync(counts_out + off, p->counts.p + off, sizeof(uint16_t) * (size_t)cnt, cudaMemcpyDeviceToHost,
+                                   copy_st) != cudaSuccess)
+      rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (cudaStreamSynchronize(copy_st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    if (rc == DYNA_OK) rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: %s", cudaGetErrorString(cudaGetLastError()));
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(copy_st);
+  p->launches = launches;
+  return rc;
+}
+
 extern "C" int64_t dyna_mh_plan_pairs(const dyna_mh_plan* p) { return p ? p->pairs : 0; }
 extern "C" int dyna_mh_plan_launches(const dyna_mh_plan* p) { return p ? p->launches : 0; }
 extern "C" void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan* p) { return p ? p->counts.p : nullptr; }

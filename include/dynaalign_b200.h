@@ -141,6 +141,9 @@ DYNA_API int dyna_mh_plan_upload_sequences(dyna_mh_plan*, const uint8_t* residue
 DYNA_API int dyna_mh_plan_upload_signatures(dyna_mh_plan*, const uint32_t* sig, void* stream);
 DYNA_API int dyna_mh_plan_run_signatures(dyna_mh_plan*, void* stream); /* K1 + layout transform */
 DYNA_API int dyna_mh_plan_run_match(dyna_mh_plan*, void* stream);      /* K3 over the plan's row range */
+/* run_match + fetch_counts fused: row chunks are copied to the host (pinned memory recommended) while the next chunks
+ * are still being matched */
+DYNA_API int dyna_mh_plan_run_match_fetch(dyna_mh_plan*, uint16_t* counts_tri_out, void* stream);
 DYNA_API int dyna_mh_plan_fetch_signatures(dyna_mh_plan*, uint32_t* sig_out, void* stream);
 DYNA_API int dyna_mh_plan_fetch_counts(dyna_mh_plan*, uint16_t* counts_tri_out, void* stream);
 /* Child plan over a subset of the parent's sequences (clusterbreak's recursion re-invokes sim_fn on each oversized

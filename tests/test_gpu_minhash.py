@@ -224,3 +224,20 @@ def test_device_vocabulary_and_full_gpu_minhash(evp):
     assert same_matrix(got["dist_matrix"], want["dist_matrix"])
     with pytest.raises(da.DynaAlignError, match="'k' must be a positive integer between 1 and 2"):
         da.vocab_ranks(["ACDE", "AC", "ACDEF"], 3)
+
+
+def test_overlapped_match_fetch_equals_plain():
+    from dynaalign_b200 import synth
+    seqs = [s.decode() for s in synth.peptides_clustered(20000, children=50)]
+    plan = da.MinHashPlan(seqs, 4, 64, seed=7)
+    a = plan.match_counts()          # chunked + overlapped (170 MB of counts -> several chunks)
+    b = plan.match_counts()          # plain fetch of the same device buffer
+    assert (a == b).all()
+    sig = plan.signatures()
+    pick = np.random.default_rng(0).integers(0, len(a), 5000)
+    n = len(seqs)
+    # invert the packed index for a sample and recount from the signatures
+    i = (n - 2 - np.floor(np.sqrt(-8.0 * pick + 4.0 * n * (n - 1) - 7) / 2.0 - 0.5)).astype(np.int64)
+    j = (pick + i + 1 - n * (n - 1) // 2 + (n - i) * ((n - i) - 1) // 2).astype(np.int64)
+    assert ((sig[i] == sig[j]).sum(axis=1) == a[pick]).all()
+    plan.close()
