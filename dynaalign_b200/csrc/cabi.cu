@@ -470,7 +470,8 @@ extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
 // NW plan
 // =====================================================================================================
 struct NwClass {
-  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit
+  int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit,
+             // 6 two-pairs-per-warp 16-bit, several passes
   int R;
   std::vector<NwUnit> units;
   DevBuf<NwUnit> d_units;
@@ -489,6 +490,7 @@ struct dyna_nw_plan {
   DevBuf<int8_t> sub;
   DevBuf<uint32_t> matches, length;
   DevBuf<int32_t> scratch;
+  DevBuf<uint4> scratch2;  // packed multi-pass kernel: boundary rows
 };
 
 extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int64_t* offsets, int64_t n,
@@ -549,8 +551,13 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
   auto fits16 = [&](int m) {
     const int64_t hi = (int64_t)std::max(smax, 0) * std::min<int64_t>(m, max_len) + ((int64_t)m + max_len) * gap_ext + gap_open;
-    return pack16 && m <= 32 * kNwWarp2MaxR && hi <= 32000 && (int64_t)m + max_len <= 65535;
+    return pack16 && hi <= 32000 && (int64_t)m + max_len <= 65535;
   };
+  // rows above this length take the multi-pass form of the packed kernel (strips of <= 12 rows keep the fast
+  // ping-pong / increment-table configuration); measured cross-over against the single-pass tall-strip form
+  int mp_min_rows = 32 * kNwWarp2MaxR + 1;  // 385..640 rows: single pass with tall strips measured faster (2.60 vs 2.25 TCUPS)
+  if (const char* e = getenv("DYNA_NW_MP_MINROWS")) mp_min_rows = std::max(32 * 12 + 1, atoi(e));
+  bool need_scratch2 = false;
 
   // encode residues, 32-bit offsets
   std::vector<uint8_t> codes((size_t)total + 4);
@@ -586,10 +593,14 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     const int m = (int)(offsets[i + 1] - offsets[i]);
     int kind, R, step;
     if (m == 0) { kind = 0; R = 0; step = 4096; }
-    else if (getenv("DYNA_NW_FORCE_WARP2") && fits16(m) && max_len <= kNwWarp2MaxCols) { kind = 4; R = std::max(2, nw_warp_R(m)); step = 2 * kNwWarpUnitPairs; }
+    else if (getenv("DYNA_NW_FORCE_WARP2") && fits16(m) && max_len <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = std::max(2, nw_warp_R(m)); step = 2 * kNwWarpUnitPairs; }
     else if (nw_use_thread_kernel(m) && fits16(m)) { kind = 5; R = nw_thread_R(m); step = 2 * kNwThreadUnitPairs; }
     else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
-    else if (fits16(m) && max_len <= kNwWarp2MaxCols) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
+    else if (fits16(m) && max_len <= kNwWarp2MaxCols && m >= mp_min_rows && m <= kNwWarp2MpMaxRows) {
+      const int npass = (m + 32 * 12 - 1) / (32 * 12);
+      kind = 6; R = std::max(7, (m + 32 * npass - 1) / (32 * npass)); step = 2 * kNwWarpUnitPairs; need_scratch2 = true;
+    }
+    else if (fits16(m) && max_len <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
     else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
     else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
     NwClass* c = get_class(kind, R);
@@ -601,6 +612,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
       p->matches.alloc((size_t)p->pairs) || p->length.alloc((size_t)p->pairs))
     return nullptr;
   if (need_scratch && p->scratch.alloc((size_t)kNwMultiPassGrid * 8 * 3 * (size_t)p->max_cols)) return nullptr;
+  if (need_scratch2 && p->scratch2.alloc((size_t)kNwMultiPassGrid * 32 * (size_t)kNwWarp2MaxCols)) return nullptr;
   auto cp = [&](void* dst, const void* src, size_t bytes) {
     return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
@@ -642,6 +654,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       case 2: DYNA_TRY(launch_nw_warp(c->R, p->slant, false, d, c->d_units.p, nu, nullptr, 0, st)); break;
       case 4: DYNA_TRY(launch_nw_warp2(c->R, d, c->d_units.p, nu, st)); break;
       case 5: DYNA_TRY(launch_nw_thread2(c->R, d, c->d_units.p, nu, st)); break;
+      case 6: DYNA_TRY(launch_nw_warp2mp(c->R, d, c->d_units.p, nu, p->scratch2.p, st)); break;
       default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, st)); break;
     }
     ++p->launches;

@@ -590,6 +590,185 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5x2 multi-pass: the packed two-pairs kernel for rows longer than one pass of 32*R rows (R <= 12 keeps the fast
+// ping-pong / increment-table configuration).  The CTA walks the row sequence in passes of 32*R rows; within a pass
+// every warp processes its pair-sets exactly like nw_warp2_kernel, except that
+//   * lane 0 of pass p > 0 takes its upper neighbour (H, F, statA, statB per column) from a global scratch line that
+//     lane 31 of pass p-1 wrote (in place: lane 31 writes column t-31 while lane 0 reads column t), and
+//   * results are captured in the last pass only.
+// Scratch: one 16-byte entry per column, per pair-set, per resident CTA (persistent grid).
+// ------------------------------------------------------------------------------------------------
+constexpr int kNwMpPairSets = 32;  // pair-sets (= 64 pairs) per unit at most
+
+template <int R>
+__global__ void __launch_bounds__(kWarpThreads, 2)
+nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units, uint4* __restrict__ scratch) {
+  using S = Strip<R>;
+  using L = Warp2Smem<R, 2, kWarpThreads>;
+  constexpr int nwarps = kWarpThreads / 32;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  uint32_t* prof = reinterpret_cast<uint32_t*>(smem_dyn + L::kProfOff);
+  uint32_t* incT = reinterpret_cast<uint32_t*>(smem_dyn + L::kIncOff);
+  uint8_t* stage_base = smem_dyn + L::kStageOff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.one - 1u;
+  const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // keep it a register operand (see nw_thread2_kernel)
+  const uint32_t bord2 = pack16(ge - go);
+  const unsigned full = 0xFFFFFFFFu;
+  uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwStageCols + 8);
+  uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwStageCols + 8);
+  const uint32_t* plane = prof + lane * L::kProfStride;
+  const uint32_t* ilane = incT + lane * L::kIncStride;
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row;
+    const int m = d.off[row + 1] - d.off[row];
+    const uint8_t* __restrict__ a = d.codes + d.off[row];
+    const int npass = (m + 32 * R - 1) / (32 * R);
+    const int npairs2 = (un.j_count + 1) >> 1;
+
+    for (int pass = 0; pass < npass; ++pass) {
+      const int row0 = pass * 32 * R;
+      const bool last_pass = (pass == npass - 1);
+      __syncthreads();  // previous pass (or unit) no longer reads the tables
+      build_profile<R, 32, L::kProfStride>(prof, a, m, row0, d.sub, 2 * ge, tid, kWarpThreads);
+      for (int idx = tid; idx < 32 * L::kProfStride; idx += kWarpThreads) prof[24 * 32 * L::kProfStride + idx] = 0u;
+      for (int idx = tid; idx < 25 * 32 * L::kIncStride; idx += kWarpThreads) {
+        const int cls = idx / (32 * L::kIncStride);
+        const int rem = idx - cls * (32 * L::kIncStride);
+        const int ln = rem / L::kIncStride, k = rem - ln * L::kIncStride;
+        const int r = row0 + ln * R + k;
+        incT[idx] = 1u | ((k < R && r < m && cls < 24 && a[r] == cls) ? 0x10000u : 0u);
+      }
+      __syncthreads();
+      const int lm = last_pass ? (m - 1 - row0) / R : 31;
+      const int km = (m - 1 - row0) - lm * R;
+      const int r0 = row0 + lane * R;
+
+      for (int pp = warp; pp < npairs2; pp += nwarps) {
+        int jA = un.j_begin + 2 * pp;
+        int jB = jA + 1;
+        const bool hasB = (jB < un.j_begin + un.j_count);
+        if (!hasB) jB = jA;
+        int nA = d.off[jA + 1] - d.off[jA], nB = d.off[jB + 1] - d.off[jB];
+        if (nB > nA) {
+          int tj = jA; jA = jB; jB = tj;
+          int tn = nA; nA = nB; nB = tn;
+        }
+        uint4* __restrict__ scr = scratch + ((int64_t)blockIdx.x * kNwMpPairSets + pp) * kNwStageCols;
+        {
+          const uint8_t* __restrict__ bA = d.codes + d.off[jA];
+          const uint8_t* __restrict__ bB = d.codes + d.off[jB];
+          __syncwarp();
+          for (int q = lane; q < nA; q += 32) {
+            sA[q] = bA[q];
+            sB[q] = (q < nB) ? bB[q] : (uint8_t)24;
+          }
+          __syncwarp();
+        }
+        uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          H0[k] = H1[k] = bord2;  // border column (slanted): the same for every row >= 1
+          El[k] = sent2;
+          SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+        }
+        uint32_t prevUpH = (r0 == 0) ? 0u : bord2;  // diagonal source (r0, 0): corner only for the very first row
+        uint32_t prevUpSA = 0u, prevUpSB = 0u;
+        uint32_t outH = 0u, outF = 0u, outSA = 0u, outSB = 0u;
+        uint32_t resB = 0u;
+        const unsigned n_act = (lane <= lm) ? (unsigned)nA : 0u;
+        const int capB = (last_pass && lane == lm) ? nB - 1 : -1;
+        const int T = nA + lm;
+        // lane 0 of a later pass reads its upper neighbour from scratch, one column ahead of its use (the load
+        // latency hides behind the current column's work)
+        const bool from_scr = (lane == 0 && pass > 0);
+        uint4 nxt = make_uint4(bord2, sent2, 0u, 0u);
+        if (from_scr && nA > 0) nxt = scr[0];
+        for (int t0 = 0; t0 < T; t0 += 2) {
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int jc = t0 + ph - lane;
+            uint32_t rH = __shfl_up_sync(full, outH, 1);
+            uint32_t rF = __shfl_up_sync(full, outF, 1);
+            uint32_t rSA = __shfl_up_sync(full, outSA, 1);
+            uint32_t rSB = __shfl_up_sync(full, outSB, 1);
+            if (lane == 0) {  // pass 0: border row (nxt stays at the border constants); later passes: scratch
+              rH = nxt.x;
+              rF = nxt.y;
+              rSA = nxt.z;
+              rSB = nxt.w;
+              if (from_scr && jc + 1 < nA) nxt = scr[jc + 1];
+            }
+            if ((unsigned)jc < n_act) {
+              const int cA = sA[jc];
+              const int cB = sB[jc];
+              uint32_t pwA[S::RW], pwB[S::RW];
+              const uint32_t* pa = plane + cA * (32 * L::kProfStride);
+              const uint32_t* pb = plane + cB * (32 * L::kProfStride);
+              const uint4* ia = reinterpret_cast<const uint4*>(ilane + cA * (32 * L::kIncStride));
+              const uint4* ib = reinterpret_cast<const uint4*>(ilane + cB * (32 * L::kIncStride));
+#pragma unroll
+              for (int w = 0; w < S::RW; ++w) {
+                pwA[w] = pa[w];
+                pwB[w] = pb[w];
+              }
+              if (ph == 0) {
+                strip_column2<R, 2>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                    ngo2, c, outF, ia, ib);
+                outH = H1[R - 1];
+                outSA = SA1[R - 1];
+                outSB = SB1[R - 1];
+              } else {
+                strip_column2<R, 2>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                    ngo2, c, outF, ia, ib);
+                outH = H0[R - 1];
+                outSA = SA0[R - 1];
+                outSB = SB0[R - 1];
+              }
+              prevUpH = rH;
+              prevUpSA = rSA;
+              prevUpSB = rSB;
+              if (!last_pass && lane == 31) scr[jc] = make_uint4(outH, outF, outSA, outSB);
+              if (jc == capB) {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                  if (k == km) resB = (ph == 0) ? SB1[k] : SB0[k];
+              }
+            }
+          }
+        }
+        if (last_pass) {
+          const bool in1 = (((lm + nA) & 1) != 0);
+          uint32_t resA = 0u;
+#pragma unroll
+          for (int k = 0; k < R; ++k)
+            if (k == km) resA = in1 ? SA1[k] : SA0[k];
+          resA = __shfl_sync(full, resA, lm);
+          resB = __shfl_sync(full, resB, lm);
+          if (lane == 0) {
+            const int64_t slotA = pair_slot(d.n, row, jA, d.slab_base);
+            d.matches[slotA] = resA >> 16;
+            d.length[slotA] = (uint32_t)(m + nA) - (resA & 0xFFFFu);
+            if (hasB) {
+              const int64_t slotB = pair_slot(d.n, row, jB, d.slab_base);
+              d.matches[slotB] = resB >> 16;
+              d.length[slotB] = (uint32_t)(m + nB) - (resB & 0xFFFFu);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: one thread per pair (rows <= R <= 32)
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreadThreads = 128;
@@ -867,6 +1046,30 @@ int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, con
 #undef DYNA_CASE
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw warp kernel: unsupported strip height %d", R);
+  }
+}
+
+template <int R>
+int launch_warp2mp_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, uint4* d_scratch, cudaStream_t st) {
+  using L = Warp2Smem<R, 2, kWarpThreads>;
+  DYNA_CUDA(cudaFuncSetAttribute(nw_warp2mp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  const int grid = std::min(num_units, kNwMultiPassGrid);
+  nw_warp2mp_kernel<R><<<grid, kWarpThreads, L::kTotal, st>>>(d, d_units, num_units, d_scratch);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_warp2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, void* d_scratch, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  uint4* scr = static_cast<uint4*>(d_scratch);
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_warp2mp_R<RR>(d, d_units, num_units, scr, st);
+    DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9) DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw warp2 multipass kernel: unsupported strip height %d", R);
   }
 }
 

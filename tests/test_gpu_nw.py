@@ -178,3 +178,16 @@ def test_short_rows_against_longer_columns_many_shapes():
         gm, gl = da.nw_pair_stats(seqs, name, go, ge)
         wm, wl = port.nw_pair_stats(seqs, name, go, ge)
         assert (gm == wm).all() and (gl == wl).all(), (seqs, name, go, ge)
+
+
+def test_packed_multipass_rows(monkeypatch):
+    # rows of 385..1500 residues: the packed kernel in several passes of 32*R rows (boundary rows through scratch)
+    rng = np.random.default_rng(17)
+    seqs = [random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0] for L in (385, 386, 640, 641, 767, 769, 1000, 1153, 1500)]
+    seqs += random_seqs(rng, 6, 1, 700, "ARNDCQEGHILKMFPSTWYV") + ["", "W" * 900]
+    rng.shuffle(seqs)
+    check_stats(seqs)
+    a = da.nw_pair_stats(seqs, "BLOSUM45", 3, 1)
+    monkeypatch.setenv("DYNA_NW_PACK16", "0")
+    b = da.nw_pair_stats(seqs, "BLOSUM45", 3, 1)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
