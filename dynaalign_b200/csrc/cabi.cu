@@ -549,10 +549,6 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // for the flat -30000 sentinel below and the "- go" of a gap opening above.
   bool pack16 = p->slant && gap_ext >= 0 && gap_open >= 0 && (smin - 3ll * gap_open + 2ll * gap_ext) >= -24000;
   if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
-  auto fits16 = [&](int m) {
-    const int64_t hi = (int64_t)std::max(smax, 0) * std::min<int64_t>(m, max_len) + ((int64_t)m + max_len) * gap_ext + gap_open;
-    return pack16 && hi <= 32000 && (int64_t)m + max_len <= 65535;
-  };
   // rows above this length take the multi-pass form of the packed kernel (strips of <= 12 rows keep the fast
   // ping-pong / increment-table configuration); measured cross-over against the single-pass tall-strip form
   int mp_min_rows = 32 * kNwWarp2MaxR + 1;  // 385..640 rows: single pass with tall strips measured faster (2.60 vs 2.25 TCUPS)
@@ -589,23 +585,55 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     return c;
   };
   bool need_scratch = false;
+  // range-maximum table over the sequence lengths: the packed (16-bit) kernels are chosen per UNIT from the longest
+  // column sequence the unit contains, so a few very long sequences do not push every pair onto the 32-bit path
+  std::vector<std::vector<int32_t>> rmq;
+  {
+    rmq.emplace_back((size_t)n);
+    for (int64_t i = 0; i < n; ++i) rmq[0][(size_t)i] = (int32_t)(offsets[i + 1] - offsets[i]);
+    for (int64_t w = 1; (2 * w) <= n; w *= 2) {
+      const std::vector<int32_t>& prev = rmq.back();
+      std::vector<int32_t> cur((size_t)(n - 2 * w + 1));
+      for (int64_t i = 0; i + 2 * w <= n; ++i) cur[(size_t)i] = std::max(prev[(size_t)i], prev[(size_t)(i + w)]);
+      rmq.push_back(std::move(cur));
+    }
+  }
+  auto range_max = [&](int64_t lo, int64_t hi) -> int64_t {  // max length over [lo, hi), hi > lo
+    int lvl = 0;
+    while ((2ll << lvl) <= hi - lo) ++lvl;
+    return std::max(rmq[(size_t)lvl][(size_t)lo], rmq[(size_t)lvl][(size_t)(hi - (1ll << lvl))]);
+  };
+  auto fits16u = [&](int m, int64_t nmax) {  // fits16() with the unit's own longest column
+    const int64_t hi = (int64_t)std::max(smax, 0) * std::min<int64_t>(m, nmax) + ((int64_t)m + nmax) * gap_ext + gap_open;
+    return pack16 && hi <= 32000 && (int64_t)m + nmax <= 65535;
+  };
+  const bool force_warp2 = getenv("DYNA_NW_FORCE_WARP2") != nullptr;
   for (int64_t i = row_begin; i < row_end; ++i) {
     const int m = (int)(offsets[i + 1] - offsets[i]);
-    int kind, R, step;
-    if (m == 0) { kind = 0; R = 0; step = 4096; }
-    else if (getenv("DYNA_NW_FORCE_WARP2") && fits16(m) && max_len <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = std::max(2, nw_warp_R(m)); step = 2 * kNwWarpUnitPairs; }
-    else if (nw_use_thread_kernel(m) && fits16(m)) { kind = 5; R = nw_thread_R(m); step = 2 * kNwThreadUnitPairs; }
-    else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
-    else if (fits16(m) && max_len <= kNwWarp2MaxCols && m >= mp_min_rows && m <= kNwWarp2MpMaxRows) {
-      const int npass = (m + 32 * 12 - 1) / (32 * 12);
-      kind = 6; R = std::max(7, (m + 32 * npass - 1) / (32 * npass)); step = 2 * kNwWarpUnitPairs; need_scratch2 = true;
+    int64_t j = i;
+    while (j < n) {
+      int kind, R, step;
+      if (m == 0) { kind = 0; R = 0; step = 4096; }
+      else {
+        // try the packed kernels on the widest unit they use; fall back to the 32-bit kernels for this stretch
+        const int pstep = nw_use_thread_kernel(m) && !force_warp2 ? 2 * kNwThreadUnitPairs : 2 * kNwWarpUnitPairs;
+        const int64_t nmax = range_max(j, std::min<int64_t>(j + pstep, n));
+        const bool p16 = fits16u(m, nmax);
+        if (force_warp2 && p16 && nmax <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = std::max(2, nw_warp_R(m)); step = pstep; }
+        else if (nw_use_thread_kernel(m) && p16) { kind = 5; R = nw_thread_R(m); step = pstep; }
+        else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
+        else if (p16 && nmax <= kNwWarp2MaxCols && m >= mp_min_rows && m <= kNwWarp2MpMaxRows) {
+          const int npass = (m + 32 * 12 - 1) / (32 * 12);
+          kind = 6; R = std::max(7, (m + 32 * npass - 1) / (32 * npass)); step = pstep; need_scratch2 = true;
+        }
+        else if (p16 && nmax <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = nw_warp_R(m); step = pstep; }
+        else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
+        else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
+      }
+      const int64_t cnt = std::min<int64_t>(step, n - j);
+      get_class(kind, R)->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
+      j += cnt;
     }
-    else if (fits16(m) && max_len <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = nw_warp_R(m); step = 2 * kNwWarpUnitPairs; }
-    else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
-    else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
-    NwClass* c = get_class(kind, R);
-    for (int64_t j = i; j < n; j += step)
-      c->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)std::min<int64_t>(step, n - j)});
   }
 
   if (p->codes.alloc(codes.size()) || p->off.alloc(off32.size()) || p->sub.alloc(576) ||

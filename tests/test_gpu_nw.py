@@ -191,3 +191,13 @@ def test_packed_multipass_rows(monkeypatch):
     monkeypatch.setenv("DYNA_NW_PACK16", "0")
     b = da.nw_pair_stats(seqs, "BLOSUM45", 3, 1)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_mixed_lengths_choose_kernels_per_unit():
+    # a few very long sequences among short ones: units without them stay on the packed kernels, units with them
+    # fall back to the 32-bit kernels -- results must not depend on which kernel a pair landed on
+    rng = np.random.default_rng(18)
+    seqs = random_seqs(rng, 150, 20, 400, "ARNDCQEGHILKMFPSTWYV")
+    for pos, L in [(3, 1500), (77, 2300), (140, 1100)]:
+        seqs[pos] = random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0]
+    check_stats(seqs)
