@@ -622,11 +622,12 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
         if (force_warp2 && p16 && nmax <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = std::max(2, nw_warp_R(m)); step = pstep; }
         else if (nw_use_thread_kernel(m) && p16) { kind = 5; R = nw_thread_R(m); step = pstep; }
         else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
-        else if (p16 && nmax <= kNwWarp2MaxCols && m >= mp_min_rows && m <= kNwWarp2MpMaxRows) {
+        else if (p16 && nmax <= kNwWarp2MaxCols && m < mp_min_rows && m <= 32 * kNwWarp2MaxR) { kind = 4; R = nw_warp_R(m); step = pstep; }
+        else if (p16 && nmax <= kNwWarp2MpMaxCols && m > 32 * 6 && m <= kNwWarp2MpMaxRows) {
+          // long rows, or columns too long for the single-pass kernel's staging buffer: the multi-pass form
           const int npass = (m + 32 * 12 - 1) / (32 * 12);
           kind = 6; R = std::max(7, (m + 32 * npass - 1) / (32 * npass)); step = pstep; need_scratch2 = true;
         }
-        else if (p16 && nmax <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = nw_warp_R(m); step = pstep; }
         else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
         else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
       }
@@ -640,7 +641,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
       p->matches.alloc((size_t)p->pairs) || p->length.alloc((size_t)p->pairs))
     return nullptr;
   if (need_scratch && p->scratch.alloc((size_t)kNwMultiPassGrid * 8 * 3 * (size_t)p->max_cols)) return nullptr;
-  if (need_scratch2 && p->scratch2.alloc((size_t)kNwMultiPassGrid * 32 * (size_t)kNwWarp2MaxCols)) return nullptr;
+  if (need_scratch2 && p->scratch2.alloc((size_t)kNwMultiPassGrid * 32 * (size_t)kNwWarp2MpMaxCols)) return nullptr;
   auto cp = [&](void* dst, const void* src, size_t bytes) {
     return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };

@@ -388,7 +388,7 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
 constexpr int kNwStageCols = 1024;
 
 // dynamic shared memory layout of nw_warp2_kernel
-template <int R, int VAR, int THREADS>
+template <int R, int VAR, int THREADS, int STAGE = kNwStageCols>
 struct Warp2Smem {
   // increment-table stride per lane strip: a multiple of 4 words (128-bit loads) and an ODD multiple (conflict-free
   // across the 8 lanes of a quarter warp): 4, 12 or 20
@@ -398,7 +398,7 @@ struct Warp2Smem {
   static constexpr int kProfStride = Strip<R>::RWS;
   static constexpr int kProfBytes = 25 * 32 * kProfStride * 4;
   static constexpr int kIncBytes = VAR == 2 ? 25 * 32 * kIncStride * 4 : 0;
-  static constexpr int kStageBytes = (THREADS / 32) * 2 * (kNwStageCols + 8);
+  static constexpr int kStageBytes = (THREADS / 32) * 2 * (STAGE + 8);
   static constexpr int kIncOff = 0;                                  // 16-byte aligned first
   static constexpr int kProfOff = kIncOff + kIncBytes;
   static constexpr int kStageOff = kProfOff + kProfBytes;
@@ -599,12 +599,13 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 // Scratch: one 16-byte entry per column, per pair-set, per resident CTA (persistent grid).
 // ------------------------------------------------------------------------------------------------
 constexpr int kNwMpPairSets = 32;  // pair-sets (= 64 pairs) per unit at most
+constexpr int kNwMpStageCols = 2048;  // column-sequence length limit of the multi-pass packed kernel
 
 template <int R>
 __global__ void __launch_bounds__(kWarpThreads, 2)
 nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units, uint4* __restrict__ scratch) {
   using S = Strip<R>;
-  using L = Warp2Smem<R, 2, kWarpThreads>;
+  using L = Warp2Smem<R, 2, kWarpThreads, kNwMpStageCols>;
   constexpr int nwarps = kWarpThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   uint32_t* prof = reinterpret_cast<uint32_t*>(smem_dyn + L::kProfOff);
@@ -619,8 +620,8 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // keep it a register operand (see nw_thread2_kernel)
   const uint32_t bord2 = pack16(ge - go);
   const unsigned full = 0xFFFFFFFFu;
-  uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwStageCols + 8);
-  uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwStageCols + 8);
+  uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwMpStageCols + 8);
+  uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwMpStageCols + 8);
   const uint32_t* plane = prof + lane * L::kProfStride;
   const uint32_t* ilane = incT + lane * L::kIncStride;
 
@@ -660,7 +661,7 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
           int tj = jA; jA = jB; jB = tj;
           int tn = nA; nA = nB; nB = tn;
         }
-        uint4* __restrict__ scr = scratch + ((int64_t)blockIdx.x * kNwMpPairSets + pp) * kNwStageCols;
+        uint4* __restrict__ scr = scratch + ((int64_t)blockIdx.x * kNwMpPairSets + pp) * kNwMpStageCols;
         {
           const uint8_t* __restrict__ bA = d.codes + d.off[jA];
           const uint8_t* __restrict__ bB = d.codes + d.off[jB];
@@ -1051,7 +1052,7 @@ int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, con
 
 template <int R>
 int launch_warp2mp_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, uint4* d_scratch, cudaStream_t st) {
-  using L = Warp2Smem<R, 2, kWarpThreads>;
+  using L = Warp2Smem<R, 2, kWarpThreads, kNwMpStageCols>;
   DYNA_CUDA(cudaFuncSetAttribute(nw_warp2mp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
   const int grid = std::min(num_units, kNwMultiPassGrid);
   nw_warp2mp_kernel<R><<<grid, kWarpThreads, L::kTotal, st>>>(d, d_units, num_units, d_scratch);

@@ -46,9 +46,10 @@ int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, con
 // two pairs per warp in 16-bit lanes (host guarantees the value range); R in 2..kNwWarp2MaxR
 int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 int launch_nw_thread2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
-// packed kernel, several passes of 32*R rows (R in 7..12); scratch: kNwMultiPassGrid * 32 pair-sets * kNwWarp2MaxCols * 16 bytes
+// packed kernel, several passes of 32*R rows (R in 7..12); scratch: kNwMultiPassGrid * 32 pair-sets * kNwWarp2MpMaxCols * 16 bytes
 int launch_nw_warp2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, void* d_scratch, cudaStream_t st);
 constexpr int kNwWarp2MpMaxRows = 32 * 12 * 8;  // 8 passes at most
+constexpr int kNwWarp2MpMaxCols = 2048;        // its column-sequence limit (staging buffer)
 // (matches, length) slab -> column-major doubles, both triangles (reference: src/pairwiseSeqAlign.cpp:311,349-350)
 int launch_nw_expand(const uint32_t* d_matches, const uint32_t* d_length, int64_t n, int64_t row_begin, int64_t row_end,
                      double* d_out, cudaStream_t st);

@@ -201,3 +201,10 @@ def test_mixed_lengths_choose_kernels_per_unit():
     for pos, L in [(3, 1500), (77, 2300), (140, 1100)]:
         seqs[pos] = random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0]
     check_stats(seqs)
+
+
+def test_columns_between_1024_and_2048_use_the_multipass_packed_kernel():
+    rng = np.random.default_rng(19)
+    seqs = random_seqs(rng, 30, 200, 640, "ARNDCQEGHILKMFPSTWYV")
+    seqs += [random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0] for L in (1025, 1300, 1600, 2048, 2049)]
+    check_stats(seqs)
