@@ -208,3 +208,14 @@ def test_columns_between_1024_and_2048_use_the_multipass_packed_kernel():
     seqs = random_seqs(rng, 30, 200, 640, "ARNDCQEGHILKMFPSTWYV")
     seqs += [random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0] for L in (1025, 1300, 1600, 2048, 2049)]
     check_stats(seqs)
+
+
+def test_int16_range_boundary_of_the_packed_kernels():
+    # slanted scores of identical tryptophan runs reach 11*L + 2*L*4 (+ go): just inside and just outside the int16 guard
+    seqs = ["W" * 1600, "W" * 1680, "W" * 1690, "W" * 1450 + "A" * 200, "WY" * 700]
+    check_stats(seqs)
+    check_stats(seqs[:3], "BLOSUM62", 0, 4)
+    # high gap extension: the slant grows faster than the scores
+    seqs = ["AC" * 300, "AC" * 290 + "D" * 40, "C" * 610]
+    check_stats(seqs, "BLOSUM62", 10, 25)
+    check_stats(seqs, "BLOSUM62", 10, 26)
