@@ -153,7 +153,7 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     seqs = nw_workload(min(args.nw_n, 256))
-    n_sample = 48
+    n_sample = 64
     times = []
     cells = kind = None
     for it in range(args.warmup + args.steps):
@@ -162,9 +162,9 @@ def run_reference_arm(args, rank):
             times.append(dt)
     dt = float(np.mean(times))
     value = cells / dt / 1e9
-    peps = mh_workload(4000)
+    peps = mh_workload(8000)
     cores = os.cpu_count() or 1
-    mh_rate, mh_dt, mh_pairs, _ = cpu_mh_sample(peps, 4000, cores)
+    mh_rate, mh_dt, mh_pairs, _ = cpu_mh_sample(peps, 8000, cores)
     line = {
         "impl": "reference", "metric": "nw_allpairs_gcups", "value": value, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -176,7 +176,7 @@ def run_reference_arm(args, rank):
                                    "single-threaded in the reference" % (n_sample, n_sample * (n_sample + 1) // 2, cells)},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "minhash": {"metric": "minhash_pairs_per_sec", "value": mh_rate, "unit": "pairs/s", "cores": cores,
-                    "sample": "first 4000 peptides of config 4 (%d pairs), k=4 n_hash=500, signature build included" % mh_pairs},
+                    "sample": "first 8000 peptides of config 4 (%d pairs), k=4 n_hash=500, signature build included" % mh_pairs},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -383,14 +383,14 @@ def main():
     cpu = None
     cpu_mh = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        gc, dt, cells, kind = cpu_nw_sample(seqs, 48)
+        gc, dt, cells, kind = cpu_nw_sample(seqs, 128)
         cpu = {"value": gc, "unit": "GCUPS", "cores": 1, "kind": kind,
-               "sample": "reference similarityNW on the first 48 sequences of config 5 (1176 pairs, %.3g cells, %.1f s); "
+               "sample": "reference similarityNW on the first 128 sequences of config 5 (8256 pairs, %.3g cells, %.1f s); "
                          "the reference NW is single-threaded" % (cells, dt)}
         cores = os.cpu_count() or 1
-        rate, dt, pairs, kind = cpu_mh_sample(peps, 4000, cores)
+        rate, dt, pairs, kind = cpu_mh_sample(peps, 12000, cores)
         cpu_mh = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
-                  "sample": "reference similarityMH on the first 4000 peptides of config 4 (%d pairs, %.1f s), OpenMP on all host cores" % (pairs, dt)}
+                  "sample": "reference similarityMH on the first 12000 peptides of config 4 (%d pairs, %.1f s), OpenMP on all host cores" % (pairs, dt)}
 
     # ================================================================== BASELINE configs 1-3 through the drop-in API (rank 0)
     other = None

@@ -774,11 +774,13 @@ extern "C" void dyna_aa_index_table(int8_t* out256) { memcpy(out256, tables().aa
 // =====================================================================================================
 // MinHash host entry points
 // =====================================================================================================
+static int plan_error_code_mh() { return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA; }
+
 extern "C" int dyna_mh_signatures_murmur3(const uint8_t* residues, const int64_t* offsets, int64_t n, int k,
                                           const uint32_t* seeds, int n_hash, uint32_t* sig_out) {
   DYNA_TRY(check_mh_args(n, k, n_hash));
   dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, 0, g_device);
-  if (!p) return DYNA_ERR_CUDA;
+  if (!p) return plan_error_code_mh();
   int rc = dyna_mh_plan_upload_sequences(p, residues, offsets, k, seeds, nullptr);
   if (rc == DYNA_OK) rc = dyna_mh_plan_run_signatures(p, nullptr);
   if (rc == DYNA_OK) rc = dyna_mh_plan_fetch_signatures(p, sig_out, nullptr);
@@ -822,7 +824,7 @@ extern "C" int dyna_mh_match_counts(const uint32_t* sig, int64_t n, int n_hash, 
   if (n_hash <= 0) return fail(DYNA_ERR_INVALID, "Number of hash functions must be positive");
   if (n_hash > 65535) return fail(DYNA_ERR_UNSUPPORTED, "n_hash > 65535 is not supported (match counts are 16-bit)");
   dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, row_begin, row_end, g_device);
-  if (!p) return err_slot().empty() ? DYNA_ERR_CUDA : (err_slot().find("CUDA") != std::string::npos ? DYNA_ERR_CUDA : DYNA_ERR_INVALID);
+  if (!p) return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA;
   int rc = dyna_mh_plan_upload_signatures(p, sig, nullptr);
   if (rc == DYNA_OK) rc = dyna_mh_plan_run_match(p, nullptr);
   if (rc == DYNA_OK) rc = dyna_mh_plan_fetch_counts(p, counts_tri_out, nullptr);
@@ -927,7 +929,7 @@ extern "C" int dyna_mh_match_matrix(const uint32_t* sig, int64_t n, int n_hash, 
   if (n < 2 * 128 * gpus) gpus = 1;
   if (gpus == 1) {
     dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
-    if (!p) return DYNA_ERR_CUDA;
+    if (!p) return plan_error_code_mh();
     int rc = dyna_mh_plan_upload_signatures(p, sig, nullptr);
     if (rc == DYNA_OK) rc = mh_matrix_single(p, kind, out);
     dyna_mh_plan_destroy(p);
@@ -956,7 +958,7 @@ extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets
   };
   if (gpus == 1) {
     dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
-    if (!p) return DYNA_ERR_CUDA;
+    if (!p) return plan_error_code_mh();
     int rc = prepare(p);
     if (rc == DYNA_OK) rc = mh_matrix_single(p, DYNA_MH_SIMILARITY, out);
     dyna_mh_plan_destroy(p);
@@ -987,10 +989,7 @@ extern "C" int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offset
   PhaseTimer tm;
   dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, g_device);
   tm.lap("nw plan create");
-  if (!p) return err_slot().find("CUDA") != std::string::npos ? DYNA_ERR_CUDA
-                 : (err_slot().find("not supported") != std::string::npos || err_slot().find("exceed") != std::string::npos)
-                     ? DYNA_ERR_UNSUPPORTED
-                     : DYNA_ERR_INVALID;
+  if (!p) return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA;
   int rc = dyna_nw_plan_run(p, nullptr);
   if (tm.on) cudaDeviceSynchronize();
   tm.lap("nw kernels");
@@ -1013,12 +1012,7 @@ void nw_expand_host(const uint32_t* matches, const uint32_t* length, int64_t n, 
     }
   }
 }
-int plan_error_code() {
-  const std::string& e = err_slot();
-  if (e.find("CUDA") != std::string::npos) return DYNA_ERR_CUDA;
-  if (e.find("not supported") != std::string::npos || e.find("exceed") != std::string::npos) return DYNA_ERR_UNSUPPORTED;
-  return DYNA_ERR_INVALID;
-}
+int plan_error_code() { return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA; }  // code of the failed plan creation
 }  // namespace
 
 extern "C" int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,

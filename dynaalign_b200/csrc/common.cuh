@@ -18,6 +18,10 @@ inline std::string& err_slot() {
   static thread_local std::string e;
   return e;
 }
+inline int& err_code_slot() {
+  static thread_local int c = 0;
+  return c;
+}
 inline int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -25,6 +29,7 @@ inline int fail(int code, const char* fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   err_slot() = buf;
+  err_code_slot() = code;
   return code;
 }
 

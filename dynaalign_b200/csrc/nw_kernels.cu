@@ -313,10 +313,11 @@ __device__ __forceinline__ uint32_t stat_select(uint32_t left, uint32_t up, uint
   return S;
 }
 
-// Variants of the per-pair statistics update (same results; VAR 1 is the default, VAR 0 kept for A/B measurements):
-//   VAR 0: SEL + predicated add                       (10 ALU-pipe instructions per two cells)  2.51 TCUPS
-//   VAR 1: select done with three 2-input adds        ( 8 ALU-pipe instructions per two cells)  2.64 TCUPS
-// (A third variant that derived both increments from one permute through IMAD / IMAD.HI was slower: 2.38 TCUPS.)
+// Variants of the per-pair statistics update (same results):
+//   VAR 1: increments (1 | eq << 16) permuted out of the profile word (two PRMT per two cells); select by three adds
+//   VAR 2: increments read ready-made from a shared-memory table, 128 bits per four rows (strips R <= 12)
+// (Measured and dropped: SEL + predicated add, 2.51 vs 2.64 TCUPS; both increments from one permute through
+//  IMAD / IMAD.HI, 2.38 TCUPS.)
 struct Stat2Consts {
   uint32_t one, zero;
 };
@@ -353,16 +354,8 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
     bool puB, puA, pdB, pdA;
     const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);   // pred_hi -> pair B, pred_lo -> pair A
     const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
-    uint32_t SA, SB;
-    if (VAR == 0) {
-      SA = puA ? upSA : SAo[k];
-      if (pdA) SA = dSA + incA;
-      SB = puB ? upSB : SBo[k];
-      if (pdB) SB = dSB + incB;
-    } else {
-      SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
-      SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
-    }
+    const uint32_t SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
     diagH = Ho[k];
     dSA = SAo[k];
     dSB = SBo[k];
