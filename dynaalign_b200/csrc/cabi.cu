@@ -774,6 +774,19 @@ extern "C" void dyna_aa_index_table(int8_t* out256) { memcpy(out256, tables().aa
 // =====================================================================================================
 // MinHash host entry points
 // =====================================================================================================
+namespace {
+struct PhaseTimer {  // DYNA_TIMING=1: per-phase wall clock of the host entry points on stderr
+  bool on = getenv("DYNA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dyna timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 static int plan_error_code_mh() { return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA; }
 
 extern "C" int dyna_mh_signatures_murmur3(const uint8_t* residues, const int64_t* offsets, int64_t n, int k,
@@ -957,11 +970,17 @@ extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets
     return rc;
   };
   if (gpus == 1) {
+    PhaseTimer tm;
     dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
     if (!p) return plan_error_code_mh();
+    tm.lap("mh plan create");
     int rc = prepare(p);
+    if (tm.on) cudaDeviceSynchronize();
+    tm.lap("mh upload + signatures");
     if (rc == DYNA_OK) rc = mh_matrix_single(p, DYNA_MH_SIMILARITY, out);
+    tm.lap("mh match + expand + D2H");
     dyna_mh_plan_destroy(p);
+    tm.lap("mh plan destroy");
     return rc;
   }
   return mh_matrix_multi(n, n_hash, DYNA_MH_SIMILARITY, gpus, out, prepare);
@@ -970,19 +989,6 @@ extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets
 // =====================================================================================================
 // NW host entry points
 // =====================================================================================================
-namespace {
-struct PhaseTimer {  // DYNA_TIMING=1: per-phase wall clock of the host entry points on stderr
-  bool on = getenv("DYNA_TIMING") != nullptr;
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  void lap(const char* what) {
-    if (!on) return;
-    auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[dyna timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
-}  // namespace
-
 extern "C" int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
                                   int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint32_t* matches_out,
                                   uint32_t* length_out) {
