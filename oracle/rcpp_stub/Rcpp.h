@@ -6,7 +6,7 @@
 // It provides only the Rcpp surface those two files touch:
 //   Rcpp::stop / Rcpp::warning (printf-like, %s with std::string, %c, %d)
 //   CharacterVector: (n) ctor, length(), operator[] (read as string, assign string)
-//   NumericMatrix:   (r,c) ctor zero-filled column-major, operator()(i,j), attr("dimnames") = ...
+//   NumericMatrix:   (r,c) ctor zero-filled column-major, operator()(i,j), attr("dimnames") = ..., attr(name) = double
 //   List::create(a, b), as<std::string>(elem)
 //   IntegerVector / NumericVector / IntegerMatrix (only what rpkg/src/dyna_shims.cpp needs, for the shim harness)
 // Nothing here mirrors Rcpp's implementation; it is a behavioural stub.
@@ -98,9 +98,11 @@ class NumericMatrix {
   std::size_t nr_, nc_;
   std::vector<double> d_;
   List dimnames_;
+  double scalar_attr_ = 0.0;
   struct AttrProxy {
     NumericMatrix* m;
     AttrProxy& operator=(const List& l) { m->dimnames_ = l; return *this; }
+    AttrProxy& operator=(double v) { m->scalar_attr_ = v; return *this; }  // the one scalar attribute the shims set
   };
 public:
   NumericMatrix() : nr_(0), nc_(0) {}
@@ -113,6 +115,7 @@ public:
   const double* begin() const { return d_.data(); }
   double* begin() { return d_.data(); }
   const List& dimnames() const { return dimnames_; }
+  double scalar_attr() const { return scalar_attr_; }
 };
 
 // --- plain vectors / integer matrix (shim harness only) -------------------------

@@ -19,3 +19,9 @@ similarityNW <- function(sequences, matrixName = "BLOSUM62", gapOpen = 10L, gapE
 .mh_distance_matrix <- function(codes) {
     .Call(`_DynaAlign_mh_distance_matrix`, codes)
 }
+
+#' similarityMH + clusterbreak's quantile threshold, as an edge list (from, to, weight) instead of a dense matrix
+#' @export
+similarityMH_edges <- function(sequences, k = 4L, n_hash = 50L, thresh_p = 0.8) {
+    .Call(`_DynaAlign_similarityMH_edges`, sequences, k, n_hash, thresh_p)
+}

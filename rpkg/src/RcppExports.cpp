@@ -1,7 +1,7 @@
 // Routine registration for the DynaAlign shared object.  The first two entries are byte-for-byte the reference's
 // symbols and arities (_DynaAlign_similarityMH/3, _DynaAlign_similarityNW/4; its src/RcppExports.cpp:15,28,41-45),
 // so `useDynLib(DynaAlign, .registration = TRUE)` and the R stubs are unchanged.  Two internal entries serve the
-// GPU halves of the pure-R minhash() pipeline.
+// GPU halves of the pure-R minhash() pipeline and one the sparse threshold step of clusterbreak.
 #include <Rcpp.h>
 
 using namespace Rcpp;
@@ -58,11 +58,25 @@ BEGIN_RCPP
 END_RCPP
 }
 
+NumericMatrix similarityMH_edges(CharacterVector sequences, int k, int n_hash, double thresh_p);
+RcppExport SEXP _DynaAlign_similarityMH_edges(SEXP sequencesSEXP, SEXP kSEXP, SEXP n_hashSEXP, SEXP thresh_pSEXP) {
+BEGIN_RCPP
+    Rcpp::RObject rcpp_result_gen;
+    Rcpp::traits::input_parameter< CharacterVector >::type sequences(sequencesSEXP);
+    Rcpp::traits::input_parameter< int >::type k(kSEXP);
+    Rcpp::traits::input_parameter< int >::type n_hash(n_hashSEXP);
+    Rcpp::traits::input_parameter< double >::type thresh_p(thresh_pSEXP);
+    rcpp_result_gen = Rcpp::wrap(similarityMH_edges(sequences, k, n_hash, thresh_p));
+    return rcpp_result_gen;
+END_RCPP
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_DynaAlign_similarityMH", (DL_FUNC) &_DynaAlign_similarityMH, 3},
     {"_DynaAlign_similarityNW", (DL_FUNC) &_DynaAlign_similarityNW, 4},
     {"_DynaAlign_mh_signatures_linear", (DL_FUNC) &_DynaAlign_mh_signatures_linear, 6},
     {"_DynaAlign_mh_distance_matrix", (DL_FUNC) &_DynaAlign_mh_distance_matrix, 1},
+    {"_DynaAlign_similarityMH_edges", (DL_FUNC) &_DynaAlign_similarityMH_edges, 4},
     {NULL, NULL, 0}
 };
 

@@ -84,6 +84,54 @@ NumericMatrix similarityNW(CharacterVector sequences, std::string matrixName = "
   return similarityMatrix;
 }
 
+// similarityMH followed by clusterbreak's threshold step (R/clusterbreak.R:217-221) without the dense n x n matrix:
+// returns the edges with similarity >= quantile(sim[upper.tri(sim)], thresh_p) as an (edges x 3) matrix of
+// (from, to, weight), 1-based, row-major pair order, with the threshold itself in attr(, "threshold").
+// [[Rcpp::export]]
+NumericMatrix similarityMH_edges(CharacterVector sequences, int k = 4, int n_hash = 50, double thresh_p = 0.8) {
+  const size_t n = sequences.length();
+  if (n == 0) Rcpp::stop("Input sequences vector cannot be empty");
+  if (k <= 0) Rcpp::stop("'k' must be a positive integer");
+  if (n_hash <= 0) Rcpp::stop("Number of hash functions must be positive");
+  const Flat f = flatten(sequences);
+  std::vector<uint32_t> seeds(static_cast<size_t>(n_hash));
+  const char* e = std::getenv("DYNAALIGN_SEED");
+  const uint32_t seed = e ? static_cast<uint32_t>(std::strtoul(e, nullptr, 10)) : dyna_random_seed();
+  raise_on_error(dyna_hashfamily_seeds(seed, n_hash, seeds.data()));
+  dyna_mh_plan* plan = dyna_mh_plan_create(static_cast<int64_t>(n), n_hash, 0, static_cast<int64_t>(n), 0);
+  if (!plan) Rcpp::stop("%s", std::string(dyna_last_error()));
+  std::vector<uint64_t> hist(static_cast<size_t>(n_hash) + 1, 0);
+  std::vector<int32_t> ei, ej;
+  std::vector<uint16_t> ec;
+  double threshold = 0.0;
+  int64_t n_edges = 0;
+  int rc = dyna_mh_plan_upload_sequences(plan, f.residues.data(), f.offsets.data(), k, seeds.data(), nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_run_signatures(plan, nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_run_match(plan, nullptr);
+  if (rc == DYNA_OK) rc = dyna_mh_plan_count_histogram(plan, hist.data(), nullptr);
+  int min_count = 0;
+  if (rc == DYNA_OK) rc = dyna_quantile_type7_counts(hist.data(), n_hash, thresh_p, &threshold, &min_count);
+  if (rc == DYNA_OK) {
+    uint64_t cap = 0;
+    for (int c = min_count > 1 ? min_count : 1; c <= n_hash; ++c) cap += hist[static_cast<size_t>(c)];
+    ei.resize(cap ? cap : 1);
+    ej.resize(cap ? cap : 1);
+    ec.resize(cap ? cap : 1);
+    rc = dyna_mh_plan_threshold_edges(plan, min_count, static_cast<int64_t>(cap), ei.data(), ej.data(), ec.data(), &n_edges,
+                                      nullptr);
+  }
+  dyna_mh_plan_destroy(plan);  // released before any R error is raised
+  raise_on_error(rc);
+  NumericMatrix edges(static_cast<size_t>(n_edges), 3);
+  for (int64_t q = 0; q < n_edges; ++q) {
+    edges(q, 0) = ei[static_cast<size_t>(q)] + 1;
+    edges(q, 1) = ej[static_cast<size_t>(q)] + 1;
+    edges(q, 2) = static_cast<double>(ec[static_cast<size_t>(q)]) / n_hash;
+  }
+  edges.attr("threshold") = threshold;
+  return edges;
+}
+
 // GPU half of compute_signature_matrix (R/minHash.R): returns the n_hash x n_docs double matrix, Inf where a
 // document has no shingle.
 // [[Rcpp::export]]

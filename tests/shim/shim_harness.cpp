@@ -70,4 +70,18 @@ int shim_mh_distance_matrix(const int* codes, int n_hash, int n_docs, double* ou
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
+
+// edges come back through a caller buffer of `cap` rows; *n_edges is the real count either way
+int shim_similarityMH_edges(const char* residues, const int64_t* offsets, int64_t n, int k, int n_hash, double thresh_p,
+                            int64_t cap, double* edges_colmajor, int64_t* n_edges, double* threshold) {
+  try {
+    Rcpp::NumericMatrix m = similarityMH_edges(to_cv(residues, offsets, n), k, n_hash, thresh_p);
+    *n_edges = static_cast<int64_t>(m.nrow());
+    *threshold = m.scalar_attr();
+    if (static_cast<int64_t>(m.nrow()) <= cap)
+      for (size_t c = 0; c < 3; ++c)
+        for (size_t r = 0; r < m.nrow(); ++r) edges_colmajor[c * static_cast<size_t>(cap) + r] = m(r, c);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
 }

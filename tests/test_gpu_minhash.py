@@ -241,3 +241,61 @@ def test_overlapped_match_fetch_equals_plain():
     j = (pick + i + 1 - n * (n - 1) // 2 + (n - i) * ((n - i) - 1) // 2).astype(np.int64)
     assert ((sig[i] == sig[j]).sum(axis=1) == a[pick]).all()
     plan.close()
+
+
+def _dense_clusterbreak(pep, sim_fn, cluster_fn, thresh_p, size_max, size_min, max_itr):
+    """Literal dense-matrix restatement of cluster_recursive (R/clusterbreak.R:203-259) for the test below."""
+    from oracle.quantile_r import quantile_type7
+    state = {"rows": [], "itr": 1, "conv": 1, "filtered": []}
+
+    def rec(seqs):
+        if state["itr"] > max_itr:
+            state["conv"] = 0
+            return
+        sim = np.array(sim_fn(seqs), dtype=np.float64)
+        n = len(seqs)
+        if n > 1:
+            thr = quantile_type7(sim[np.triu_indices(n, 1)], thresh_p)
+            sim[sim < thr] = 0.0
+        gi, gj = np.nonzero(np.triu(sim))  # mode = "upper": diagonal included
+        c = np.asarray(cluster_fn(n, gi, gj, sim[gi, gj]))
+        size = np.bincount(c)[1:]
+        ids = np.arange(1, len(size) + 1)
+        big, small = ids[size > size_max], ids[size < size_min]
+        state["filtered"] += [seqs[t] for t in range(n) if c[t] in small]
+        label = state["itr"]
+        state["rows"] += [(seqs[t], "%d.%d" % (label, c[t])) for t in range(n) if c[t] not in small and c[t] not in big]
+        order = []
+        for t in range(n):
+            if c[t] in big and c[t] not in order:
+                order.append(c[t])
+        for cid in order:
+            state["itr"] += 1
+            rec([seqs[t] for t in range(n) if c[t] == cid])
+
+    rec(list(pep))
+    return state
+
+
+def _weighted_degree_mod3(n, i, j, w):
+    # test-only cluster_fn: sensitive to every edge and weight, and splits any set into <= 3 parts so the recursion ends
+    d = np.zeros(n)
+    np.add.at(d, i, w)
+    np.add.at(d, j, w)
+    return 1 + (np.rint(d * 50).astype(np.int64) % 3)
+
+
+@pytest.mark.parametrize("cluster_fn,size_max,max_itr", [("components", 40, 60), ("components", 25, 6), ("degree", 40, 10000),
+                                                         ("degree", 100, 10000)])
+def test_clusterbreak_on_device_plans_equals_dense_recursion(evp, cluster_fn, size_max, max_itr):
+    # the whole caller loop (sim_fn -> quantile -> threshold -> netcluster -> recurse) from device-resident plans
+    # gives the same clusters, labels, filtered sequences and convergence flag as the dense restatement driven by
+    # the oracle's similarity matrices
+    fn = da.connected_components if cluster_fn == "components" else _weighted_degree_mod3
+    want = _dense_clusterbreak(evp, lambda s: port.similarityMH(s, 2, 50, 42), fn, 0.8, size_max, 3, max_itr)
+    got = da.clusterbreak(evp, fn, thresh_p=0.8, size_max=size_max, size_min=3, max_itr=max_itr, k=2, n_hash=50, seed=42,
+                          verbose=False)
+    assert [tuple(r) for r in got["clustered_seq"]] == want["rows"]
+    assert got["filtered_seq"] == want["filtered"]
+    assert got["convergence"] == want["conv"] and got["calls"] == want["itr"]
+    assert want["itr"] > 1  # the recursion was exercised

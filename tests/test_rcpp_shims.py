@@ -101,3 +101,41 @@ def test_shim_r_pipeline_halves():
     d = np.zeros((4, 4), dtype=np.float64, order="F")
     rc = harness().shim_mh_distance_matrix(codes.ctypes.data_as(C.POINTER(C.c_int)), 100, 4, d.ctypes.data_as(C.POINTER(C.c_double)))
     assert rc == 0 and same_matrix(d, R.compute_distance_matrix(want_sig))
+
+
+def call_mh_edges(seqs, k, n_hash, p, cap):
+    res, off = flatten(seqs)
+    edges = np.zeros((max(cap, 1), 3), dtype=np.float64, order="F")
+    ne, thr = C.c_int64(0), C.c_double(0)
+    rc = harness().shim_similarityMH_edges(res.ctypes.data_as(C.c_char_p), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           C.c_int64(len(seqs)), k, n_hash, C.c_double(p), C.c_int64(cap),
+                                           edges.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ne), C.byref(thr))
+    if rc:
+        raise RuntimeError(harness().shim_last_error().decode())
+    return thr.value, edges[:ne.value]
+
+
+def test_shim_edges_raise_reference_errors(golden):
+    e = golden["errors"]
+    for fn, key in [(lambda: call_mh_edges([], 4, 50, 0.8, 1), "mh_empty"), (lambda: call_mh_edges(["AAAA"], 0, 50, 0.8, 1), "mh_k0"),
+                    (lambda: call_mh_edges(["AAAA"], 4, 0, 0.8, 1), "mh_nhash0")]:
+        with pytest.raises(RuntimeError) as ei:
+            fn()
+        assert str(ei.value) == e[key]
+
+
+@pytest.mark.gpu
+def test_shim_similarityMH_edges_is_the_thresholded_reference_matrix(monkeypatch, evp):
+    # R/clusterbreak.R:219-221 on the reference's own matrix: threshold <- quantile(upper.tri, p); sim[sim < threshold] <- 0
+    from oracle.quantile_r import quantile_type7
+    monkeypatch.setenv("DYNAALIGN_SEED", "42")
+    full = port.similarityMH(evp, 2, 50, 42)
+    n = len(evp)
+    for p in (0.8, 0.99):
+        want_thr = quantile_type7(full[np.triu_indices(n, 1)], p)
+        dense = full.copy()
+        dense[dense < want_thr] = 0.0
+        wi, wj = np.nonzero(np.triu(dense, 1))
+        thr, edges = call_mh_edges(evp, 2, 50, p, n * n // 2)
+        assert thr == want_thr
+        assert (edges[:, 0] == wi + 1).all() and (edges[:, 1] == wj + 1).all() and (edges[:, 2] == dense[wi, wj]).all()
