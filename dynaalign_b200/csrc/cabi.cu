@@ -21,6 +21,17 @@
 using namespace dyna;
 
 namespace {
+struct PhaseTimer {  // DYNA_TIMING=1: per-phase wall clock of the host entry points on stderr
+  bool on = getenv("DYNA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dyna timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 
 thread_local int g_device = 0;
 
@@ -498,6 +509,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
                                              int64_t row_end, int device) {
   // argument checks in the reference's order: substitution matrix name first (src/pairwiseSeqAlign.cpp:338), then
   // residues as the pair loop meets them
+  PhaseTimer timer;
   const int t = matrix_name ? find_table(matrix_name) : -1;
   if (t < 0) {
     fail(DYNA_ERR_INVALID, "Invalid substitution matrix name: %s", matrix_name ? matrix_name : "(null)");
@@ -525,7 +537,9 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     fail(DYNA_ERR_UNSUPPORTED, "gap penalties / sequence lengths exceed the exact int32 range of the DP");
     return nullptr;
   }
+  timer.lap("nw plan: validation");
   if (use_device(device) != DYNA_OK) return nullptr;
+  timer.lap("nw plan: device");
 
   std::unique_ptr<dyna_nw_plan> p(new dyna_nw_plan);
   p->device = device;
@@ -637,11 +651,13 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     }
   }
 
+  timer.lap("nw plan: work units");
   if (p->codes.alloc(codes.size()) || p->off.alloc(off32.size()) || p->sub.alloc(576) ||
       p->matches.alloc((size_t)p->pairs) || p->length.alloc((size_t)p->pairs))
     return nullptr;
   if (need_scratch && p->scratch.alloc((size_t)kNwMultiPassGrid * 8 * 3 * (size_t)p->max_cols)) return nullptr;
   if (need_scratch2 && p->scratch2.alloc((size_t)kNwMultiPassGrid * 32 * (size_t)kNwWarp2MpMaxCols)) return nullptr;
+  timer.lap("nw plan: device buffers");
   auto cp = [&](void* dst, const void* src, size_t bytes) {
     return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
@@ -655,6 +671,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     fail(DYNA_ERR_CUDA, "DynaAlign CUDA: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
+  timer.lap("nw plan: uploads");
   return p.release();
 }
 
@@ -775,16 +792,6 @@ extern "C" void dyna_aa_index_table(int8_t* out256) { memcpy(out256, tables().aa
 // MinHash host entry points
 // =====================================================================================================
 namespace {
-struct PhaseTimer {  // DYNA_TIMING=1: per-phase wall clock of the host entry points on stderr
-  bool on = getenv("DYNA_TIMING") != nullptr;
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  void lap(const char* what) {
-    if (!on) return;
-    auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[dyna timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
 }  // namespace
 
 static int plan_error_code_mh() { return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA; }

@@ -102,3 +102,40 @@ def test_config4_full_minhash_100k_peptides():
     got = (sig[ei[sel]] == sig[ej[sel]]).sum(axis=1)
     assert (got == ec[sel]).all() and (ei[sel] < ej[sel]).all()
     assert (np.diff(ei.astype(np.int64) * n + ej) > 0).all()  # row-major, strictly increasing
+
+
+def test_target_full_nw_100k_peptides():
+    # BASELINE.json's stated target: the N x N NW result for the 100,000 config-4 peptides -- 5,000,050,000 pairs
+    # (more than 2^32: every pair index has to be 64-bit), 1.28e12 cells, one GPU
+    seqs = synth.peptides_uniform(100000)
+    n = len(seqs)
+    L = lib()
+    res, off = flatten(seqs)
+    plan = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, 0, n, 0)
+    assert plan, _lib.last_error()
+    try:
+        pairs = L.dyna_nw_plan_pairs(plan)
+        assert pairs == n * (n + 1) // 2 and L.dyna_nw_plan_cells(plan) == pairs * 256
+        check(L.dyna_nw_plan_run(plan, None))
+        mt = np.zeros(pairs, dtype=np.uint32)
+        ln = np.zeros(pairs, dtype=np.uint32)
+        check(L.dyna_nw_plan_fetch(plan, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32), None))
+    finally:
+        L.dyna_nw_plan_destroy(plan)
+    idx = lambda i, j: i * n - i * (i - 1) // 2 + (j - i)
+    rows = np.arange(n, dtype=np.int64)
+    diag = rows * n - rows * (rows - 1) // 2
+    assert (mt[diag] == 16).all() and (ln[diag] == 16).all()
+    assert int(ln.min()) >= 16 and int(ln.max()) <= 32 and int(mt.max()) <= 16 and (mt <= ln).all()
+    rng = np.random.default_rng(5)
+    ii, jj = rng.integers(0, n, 1500), rng.integers(0, n, 1500)
+    sample = list(zip(np.minimum(ii, jj).tolist(), np.maximum(ii, jj).tolist()))
+    sample += [(0, n - 1), (n - 2, n - 1), (n - 1, n - 1), (61000, 61001), (99999 - 7, 99999)]
+    for a, b in sample:
+        assert (int(mt[idx(a, b)]), int(ln[idx(a, b)])) == port.nw_pair(seqs[a], seqs[b]), (a, b)
+    # a row block that straddles pair index 2^32, re-run through the host-buffer entry point
+    r0 = int(np.searchsorted(diag, 1 << 32)) - 3
+    m2, l2 = da.nw_pair_stats(seqs, row_begin=r0, row_end=r0 + 6)
+    lo = idx(r0, r0)
+    assert lo < (1 << 32) < lo + len(m2)
+    assert (m2 == mt[lo:lo + len(m2)]).all() and (l2 == ln[lo:lo + len(l2)]).all()
