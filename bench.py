@@ -376,6 +376,48 @@ def main():
     barrier()
     mh_e2e_s = max_over_ranks((time.perf_counter() - t0) / 3)
     launches += 3 * (3 + 16 * 2)
+
+    # sparse e2e: what clusterbreak consumes at this size (the dense matrix would be 80 GB) -- the type-7 quantile threshold and
+    # the edge list above it (R/clusterbreak.R:219-221).  Host buffers in, histogram + (i, j, count) edges out.
+    hist = np.zeros(n_hash + 1, dtype=np.uint64)
+    edge_cap = [0]
+    pin_ei = pin_ej = pin_ec = None
+
+    def mh_sparse_step(thresh_p=0.8):
+        nonlocal pin_ei, pin_ej, pin_ec
+        check(L.dyna_mh_plan_upload_sequences(mplan, C.cast(pin_mres.data_ptr(), C.POINTER(C.c_uint8)),
+                                              C.cast(pin_moff.data_ptr(), C.POINTER(C.c_int64)), k, ptr(seeds, C.c_uint32), st))
+        check(L.dyna_mh_plan_run_signatures(mplan, st))
+        check(L.dyna_mh_plan_run_match(mplan, st))
+        check(L.dyna_mh_plan_count_histogram(mplan, ptr(hist, C.c_uint64), st))
+        ghist = hist
+        if world > 1:  # the quantile is over all pairs: 501 counters summed across ranks (host logic, not a data-path collective)
+            t = torch.from_numpy(hist.astype(np.int64)).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ghist = t.cpu().numpy().astype(np.uint64)
+        thr, mc = C.c_double(0), C.c_int(0)
+        check(L.dyna_quantile_type7_counts(ptr(ghist, C.c_uint64), n_hash, float(thresh_p), C.byref(thr), C.byref(mc)))
+        cap = int(hist[max(mc.value, 1):].sum())
+        if pin_ei is None or cap > edge_cap[0]:
+            edge_cap[0] = cap
+            pin_ei = torch.empty(max(cap, 1), dtype=torch.int32).pin_memory()
+            pin_ej = torch.empty(max(cap, 1), dtype=torch.int32).pin_memory()
+            pin_ec = torch.empty(max(cap, 1), dtype=torch.int16).pin_memory()
+        ne = C.c_int64(0)
+        check(L.dyna_mh_plan_threshold_edges(mplan, mc.value, cap, C.cast(pin_ei.data_ptr(), C.POINTER(C.c_int32)),
+                                             C.cast(pin_ej.data_ptr(), C.POINTER(C.c_int32)),
+                                             C.cast(pin_ec.data_ptr(), C.POINTER(C.c_uint16)), C.byref(ne), st))
+        return thr.value, ne.value
+
+    mh_sparse_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        sp_thr, sp_edges = mh_sparse_step()
+    barrier()
+    mh_sparse_s = max_over_ranks((time.perf_counter() - t0) / 3)
+    sp_edges_total = sum_over_ranks(sp_edges)
+    launches += 3 * (3 + 1 + 3)
     L.dyna_mh_plan_destroy(mplan)
     mh_alg_bytes = MH_BYTES_PER_PAIR * mh_total_pairs + 4.0 * mn * n_hash * world  # every rank reads all signatures once
 
@@ -439,6 +481,10 @@ def main():
                            "l2": "inputs (2 x %.0f MB signatures) and the %.1f GB output exceed the 126 MB L2" % (4.0 * mn * mh_hrows(n_hash) / 1e6, 2.0 * mh_total_pairs / 1e9)},
                 "e2e": {"value": mh_total_pairs / mh_e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(mres.nbytes + moff.nbytes + seeds.nbytes),
                         "d2h_bytes_per_step": int(2 * mh_my_pairs), "api": "dyna_mh_plan_upload_sequences + run_signatures + run_match_fetch (chunked match, D2H overlapped)"},
+                "e2e_sparse": {"value": mh_total_pairs / mh_sparse_s, "unit": "pairs/s", "thresh_p": 0.8, "threshold": sp_thr,
+                               "edges": int(sp_edges_total), "d2h_bytes_per_step": int(10 * sp_edges + 8 * (n_hash + 1)),
+                               "api": "upload_sequences + run_signatures + run_match + count_histogram + dyna_quantile_type7_counts + "
+                                      "threshold_edges: clusterbreak's threshold step (R/clusterbreak.R:219-221) as an edge list, host buffers"},
                 "roofline": {"bound": "hbm", "achieved": mh_alg_bytes / world / (mh_match_ms * 1e-3) / 1e9,
                              "peak": peaks_hbm(), "unit": "GB/s",
                              "frac": mh_alg_bytes / world / (mh_match_ms * 1e-3) / 1e9 / peaks_hbm(),
