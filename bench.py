@@ -345,14 +345,20 @@ def main():
     mh_total_pairs = sum_over_ranks(mh_my_pairs)
     check(L.dyna_mh_plan_upload_sequences(mplan, ptr(mres, C.c_uint8), ptr(moff, C.c_int64), k, ptr(seeds, C.c_uint32), st))
 
+    # N > 1: the relabelling of the signature rows is sharded across ranks and completed by one NCCL all-gather of the
+    # code table (+ a max-reduce of the overflow gate); N = 1 (or DYNA_MH_SHARD_RELABEL=0): plain run_signatures
+    from dynaalign_b200.multirank import ShardedSignatures
+    msig = ShardedSignatures(mplan, world if os.environ.get("DYNA_MH_SHARD_RELABEL", "1") != "0" else 1, rank, dist, torch,
+                             torch.device("cuda", dev))
+
     def mh_step():
-        check(L.dyna_mh_plan_run_signatures(mplan, st))
+        msig.run(st)
         check(L.dyna_mh_plan_run_match(mplan, st))
 
     mh_ms = timed_steps(mh_step, max(args.warmup, 3), max(args.steps, 3)) / max(args.steps, 3)
     launches += 3 * max(args.steps, 3)
     # match kernel alone (the roofline kernel of this half)
-    check(L.dyna_mh_plan_run_signatures(mplan, st))
+    msig.run(st)
     mh_match_ms = timed_steps(lambda: check(L.dyna_mh_plan_run_match(mplan, st)), 1, 3) / 3
     launches += 3
     mh_pairs_s = mh_total_pairs / (mh_ms * 1e-3)
@@ -365,7 +371,7 @@ def main():
     def mh_e2e_step():
         check(L.dyna_mh_plan_upload_sequences(mplan, C.cast(pin_mres.data_ptr(), C.POINTER(C.c_uint8)),
                                               C.cast(pin_moff.data_ptr(), C.POINTER(C.c_int64)), k, ptr(seeds, C.c_uint32), st))
-        check(L.dyna_mh_plan_run_signatures(mplan, st))
+        msig.run(st)
         check(L.dyna_mh_plan_run_match_fetch(mplan, C.cast(pin_counts.data_ptr(), C.POINTER(C.c_uint16)), st))
 
     mh_e2e_step()
@@ -387,7 +393,7 @@ def main():
         nonlocal pin_ei, pin_ej, pin_ec
         check(L.dyna_mh_plan_upload_sequences(mplan, C.cast(pin_mres.data_ptr(), C.POINTER(C.c_uint8)),
                                               C.cast(pin_moff.data_ptr(), C.POINTER(C.c_int64)), k, ptr(seeds, C.c_uint32), st))
-        check(L.dyna_mh_plan_run_signatures(mplan, st))
+        msig.run(st)
         check(L.dyna_mh_plan_run_match(mplan, st))
         check(L.dyna_mh_plan_count_histogram(mplan, ptr(hist, C.c_uint64), st))
         ghist = hist
@@ -481,6 +487,8 @@ def main():
                            "l2": "inputs (2 x %.0f MB signatures) and the %.1f GB output exceed the 126 MB L2" % (4.0 * mn * mh_hrows(n_hash) / 1e6, 2.0 * mh_total_pairs / 1e9)},
                 "e2e": {"value": mh_total_pairs / mh_e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(mres.nbytes + moff.nbytes + seeds.nbytes),
                         "d2h_bytes_per_step": int(2 * mh_my_pairs), "api": "dyna_mh_plan_upload_sequences + run_signatures + run_match_fetch (chunked match, D2H overlapped)"},
+                "exchange": ("relabelling sharded by code rows; one NCCL all-gather of the %.0f MB code table + max-reduce of the overflow gate per step"
+                             % (msig.table.numel() * 4 / 1e6)) if msig.sharded else "none (every rank relabels all rows)",
                 "e2e_sparse": {"value": mh_total_pairs / mh_sparse_s, "unit": "pairs/s", "thresh_p": 0.8, "threshold": sp_thr,
                                "edges": int(sp_edges_total), "d2h_bytes_per_step": int(10 * sp_edges + 8 * (n_hash + 1)),
                                "api": "upload_sequences + run_signatures + run_match + count_histogram + dyna_quantile_type7_counts + "

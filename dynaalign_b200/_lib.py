@@ -53,6 +53,11 @@ _SIGS = {
     "dyna_mh_plan_upload_signatures": (C.c_int, [C.c_void_p, _u32p, C.c_void_p]),
     "dyna_mh_plan_run_signatures": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dyna_mh_plan_run_match": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dyna_mh_plan_run_signatures_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "dyna_mh_plan_code_rows": (C.c_int, [C.c_void_p]),
+    "dyna_mh_plan_code_row_bytes": (C.c_int64, [C.c_void_p]),
+    "dyna_mh_plan_codes_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "dyna_mh_plan_overflow_device_ptr": (C.c_void_p, [C.c_void_p]),
     "dyna_mh_plan_run_match_fetch": (C.c_int, [C.c_void_p, _u16p, C.c_void_p]),
     "dyna_mh_plan_fetch_signatures": (C.c_int, [C.c_void_p, _u32p, C.c_void_p]),
     "dyna_mh_plan_fetch_counts": (C.c_int, [C.c_void_p, _u16p, C.c_void_p]),

@@ -187,12 +187,14 @@ int mh_plan_setup16(dyna_mh_plan* p) {
 }
 
 // transpose (+ relabel when the 16-bit path is on): everything the match kernel needs, from sig[n][n_hash]
-int mh_plan_prepare_match_inputs(dyna_mh_plan* p, cudaStream_t st, int* launches) {
+int mh_plan_prepare_match_inputs(dyna_mh_plan* p, cudaStream_t st, int* launches, int code_row_begin = 0,
+                                 int code_row_end = -1) {
   DYNA_TRY(launch_mh_transpose(p->sig.p, p->n, p->n_hash, p->sigT.p, p->npitch, p->hrows, st));
   int l = 1;
   if (p->use16) {
     int lr = 0;
-    DYNA_TRY(launch_mh_relabel(p->sigT.p, p->n, p->n_hash, p->npitch, p->hrows, p->work, st, &lr));
+    if (code_row_end < 0) code_row_end = mh_hrows2(p->n_hash);
+    DYNA_TRY(launch_mh_relabel(p->sigT.p, p->n, p->n_hash, p->npitch, p->hrows, p->work, code_row_begin, code_row_end, st, &lr));
     l += lr;
   }
   if (launches) *launches = l;
@@ -272,6 +274,28 @@ extern "C" int dyna_mh_plan_run_signatures(dyna_mh_plan* p, void* stream) {
   p->launches = 1 + l;
   return DYNA_OK;
 }
+
+// Multi-rank form (all-gather variant): signatures and the layout transform for every hash row, the
+// 16-bit relabelling only for this rank's share of the packed code rows.
+extern "C" int dyna_mh_plan_run_signatures_shard(dyna_mh_plan* p, int code_row_begin, int code_row_end, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (!p->have_sequences) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_signatures_shard: no sequences uploaded");
+  if (!p->use16) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_signatures_shard: the plan has no code table (dyna_mh_plan_code_rows() == 0)");
+  if (code_row_begin < 0 || code_row_end < code_row_begin || code_row_end > mh_hrows2(p->n_hash))
+    return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_signatures_shard: bad code row range");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
+  int l = 0;
+  DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l, code_row_begin, code_row_end));
+  p->have_sig = p->have_sigT = true;
+  p->launches = 1 + l;
+  return DYNA_OK;
+}
+extern "C" int dyna_mh_plan_code_rows(const dyna_mh_plan* p) { return (p && p->use16) ? mh_hrows2(p->n_hash) : 0; }
+extern "C" int64_t dyna_mh_plan_code_row_bytes(const dyna_mh_plan* p) { return p ? (int64_t)sizeof(uint32_t) * p->npitch : 0; }
+extern "C" void* dyna_mh_plan_codes_device_ptr(dyna_mh_plan* p) { return (p && p->use16) ? p->sigP.p : nullptr; }
+extern "C" void* dyna_mh_plan_overflow_device_ptr(dyna_mh_plan* p) { return (p && p->use16) ? p->overflow.p : nullptr; }
 
 extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");

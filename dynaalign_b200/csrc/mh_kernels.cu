@@ -520,10 +520,11 @@ __global__ void mh_iota_kernel(uint32_t* __restrict__ vals, int64_t npitch, int 
 
 __global__ void __launch_bounds__(1024)
 mh_rank_scatter_kernel(const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ idx_sorted, int64_t n,
-                       int64_t npitch, uint16_t* __restrict__ sigP16, int* __restrict__ overflow, uint32_t max_codes) {
+                       int64_t npitch, uint16_t* __restrict__ sigP16, int* __restrict__ overflow, uint32_t max_codes,
+                       int h_begin) {
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t chunk_tot;
-  const int h = blockIdx.x;
+  const int h = h_begin + blockIdx.x;
   const uint32_t* keys = keys_sorted + (int64_t)h * npitch;
   const uint32_t* idx = idx_sorted + (int64_t)h * npitch;
   uint16_t* out = sigP16 + 2 * ((int64_t)(h >> 1) * npitch) + (h & 1);
@@ -788,18 +789,26 @@ int launch_mh_iota(uint32_t* d_vals, int64_t npitch, int rows, cudaStream_t st) 
 }
 
 int launch_mh_relabel(const uint32_t* d_sigT, int64_t n, int n_hash, int64_t npitch, int hrows, const MhRelabelWork& w,
-                      cudaStream_t st, int* launches) {
+                      int code_row_begin, int code_row_end, cudaStream_t st, int* launches) {
+  // code row r packs hash rows 2r and 2r+1; only the rows of [code_row_begin, code_row_end) are produced (a rank of
+  // a multi-GPU run relabels its share and all-gathers the rest)
+  const int h_begin = 2 * code_row_begin, h_end = std::min(2 * code_row_end, n_hash);
+  if (launches) *launches = 0;
+  DYNA_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+  if (code_row_end <= code_row_begin) return DYNA_OK;
+  DYNA_CUDA(cudaMemsetAsync(w.sigP + (size_t)code_row_begin * (size_t)npitch, 0,
+                            sizeof(uint32_t) * (size_t)npitch * (size_t)(code_row_end - code_row_begin), st));
+  if (h_end <= h_begin) return DYNA_OK;  // padding rows only
   // sort every hash row (value, sequence index); rows h >= n_hash are padding and are not touched
   size_t bytes = w.temp_bytes;
   cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairs(w.temp, bytes, d_sigT, w.keys_out, w.vals_in, w.vals_out,
-                                                           (int)(npitch * hrows), n_hash, w.seg_begin, w.seg_end, 0, 32, st);
+                                                           (int)(npitch * hrows), h_end - h_begin, w.seg_begin + h_begin,
+                                                           w.seg_end + h_begin, 0, 32, st);
   if (e != cudaSuccess) return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: segmented sort failed: %s", cudaGetErrorString(e));
-  DYNA_CUDA(cudaMemsetAsync(w.sigP, 0, sizeof(uint32_t) * (size_t)npitch * (size_t)mh_hrows2(n_hash), st));
-  DYNA_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
   uint32_t max_codes = (uint32_t)kMaxCodes;
   if (const char* e = getenv("DYNA_MH_MAXCODES")) max_codes = std::min<uint32_t>(max_codes, (uint32_t)atoi(e));  // tests: force the fallback
-  mh_rank_scatter_kernel<<<n_hash, 1024, 0, st>>>(w.keys_out, w.vals_out, n, npitch, reinterpret_cast<uint16_t*>(w.sigP),
-                                                  w.overflow, max_codes);
+  mh_rank_scatter_kernel<<<h_end - h_begin, 1024, 0, st>>>(w.keys_out, w.vals_out, n, npitch,
+                                                           reinterpret_cast<uint16_t*>(w.sigP), w.overflow, max_codes, h_begin);
   DYNA_CUDA(cudaGetLastError());
   if (launches) *launches = 1;
   return DYNA_OK;

@@ -48,7 +48,7 @@ int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_has
 size_t mh_relabel_temp_bytes(int64_t npitch, int hrows);
 int launch_mh_iota(uint32_t* d_vals, int64_t npitch, int rows, cudaStream_t st);
 int launch_mh_relabel(const uint32_t* d_sigT, int64_t n, int n_hash, int64_t npitch, int hrows, const MhRelabelWork& w,
-                      cudaStream_t st, int* launches);
+                      int code_row_begin, int code_row_end, cudaStream_t st, int* launches);
 // expand a counts slab into the column-major double matrix (both triangles + diagonal of the slab's rows):
 // out = table[count]; the n_hash+1 table entries are computed on the host with the reference's arithmetic
 int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,

@@ -141,6 +141,18 @@ DYNA_API int dyna_mh_plan_upload_sequences(dyna_mh_plan*, const uint8_t* residue
 DYNA_API int dyna_mh_plan_upload_signatures(dyna_mh_plan*, const uint32_t* sig, void* stream);
 DYNA_API int dyna_mh_plan_run_signatures(dyna_mh_plan*, void* stream); /* K1 + layout transform */
 DYNA_API int dyna_mh_plan_run_match(dyna_mh_plan*, void* stream);      /* K3 over the plan's row range */
+/* Multi-rank form of run_signatures (the all-gather variant of SURVEY.md section 8(e); the reference has no
+ * counterpart, src/minHash.cpp:143-157 recomputes nothing because it is one process): K1 and the layout transform
+ * run for every hash row, the exact 16-bit relabelling only for packed code rows [code_row_begin, code_row_end)
+ * out of dyna_mh_plan_code_rows() (0 = this plan matches on the 32-bit signatures and needs no exchange).  Before
+ * run_match the caller all-gathers the code table -- rows of dyna_mh_plan_code_row_bytes() bytes at
+ * dyna_mh_plan_codes_device_ptr() -- and max-reduces the int at dyna_mh_plan_overflow_device_ptr() across ranks
+ * (NCCL over NVLink in bench.py). */
+DYNA_API int dyna_mh_plan_run_signatures_shard(dyna_mh_plan*, int code_row_begin, int code_row_end, void* stream);
+DYNA_API int dyna_mh_plan_code_rows(const dyna_mh_plan*);
+DYNA_API int64_t dyna_mh_plan_code_row_bytes(const dyna_mh_plan*);
+DYNA_API void* dyna_mh_plan_codes_device_ptr(dyna_mh_plan*);
+DYNA_API void* dyna_mh_plan_overflow_device_ptr(dyna_mh_plan*);
 /* run_match + fetch_counts fused: row chunks are copied to the host (pinned memory recommended) while the next chunks
  * are still being matched */
 DYNA_API int dyna_mh_plan_run_match_fetch(dyna_mh_plan*, uint16_t* counts_tri_out, void* stream);

@@ -299,3 +299,35 @@ def test_clusterbreak_on_device_plans_equals_dense_recursion(evp, cluster_fn, si
     assert got["filtered_seq"] == want["filtered"]
     assert got["convergence"] == want["conv"] and got["calls"] == want["itr"]
     assert want["itr"] > 1  # the recursion was exercised
+
+
+@pytest.mark.parametrize("cuts", [(0, 16), (0, 5, 16), (0, 1, 2, 15, 16)])
+def test_relabelling_by_code_row_shards_equals_full(cuts, monkeypatch):
+    # multi-rank form: each rank relabels a share of the packed code rows; here the shares are produced one after the
+    # other into the same table, which must then drive the match kernel to the same counts as the unsharded plan
+    monkeypatch.setenv("DYNA_MH_PACK16", "1")
+    n, n_hash, k = 1500, 31, 3
+    seqs = [s.decode() for s in synth_peptides(n)]
+    seeds = da.hashfamily_seeds(11, n_hash)
+    want = da.mh_match_counts(port.mh_signatures(seqs, k, seeds))
+    L = _lib.lib()
+    res, off = _lib.flatten(seqs)
+    plan = L.dyna_mh_plan_create(n, n_hash, 0, n, 0)
+    assert plan, _lib.last_error()
+    try:
+        _lib.check(L.dyna_mh_plan_upload_sequences(plan, _lib.ptr(res, C.c_uint8), _lib.ptr(off, C.c_int64), k, _lib.ptr(seeds, C.c_uint32), None))
+        assert L.dyna_mh_plan_code_rows(plan) == 16 and L.dyna_mh_plan_code_row_bytes(plan) % 512 == 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            _lib.check(L.dyna_mh_plan_run_signatures_shard(plan, a, b, None))
+        _lib.check(L.dyna_mh_plan_run_match(plan, None))
+        got = np.zeros(len(want), dtype=np.uint16)
+        _lib.check(L.dyna_mh_plan_fetch_counts(plan, _lib.ptr(got, C.c_uint16), None))
+        assert (got == want).all()
+        assert L.dyna_mh_plan_run_signatures_shard(plan, 3, 17, None) != 0  # range check
+    finally:
+        L.dyna_mh_plan_destroy(plan)
+
+
+def synth_peptides(n):
+    from dynaalign_b200 import synth
+    return synth.peptides_clustered(n, children=10)

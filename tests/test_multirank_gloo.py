@@ -70,3 +70,40 @@ def test_two_ranks_tile_the_triangle():
         assert p.exitcode == 0
     assert ok_nw and ok_mh
     assert b[0] == 0 and b[-1] == 41 and mb[0] == 0 and mb[-1] == 41 and 0 < b[1] < 41 and 0 < mb[1] < 41
+
+
+def _codes_worker(rank, world, port_no, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynaalign_b200.multirank import exchange_codes, shard_bounds
+
+    rows, pitch = 16, 384
+    b = shard_bounds(rows, world, rank)
+    table = torch.full((rows, pitch), -1, dtype=torch.int32)
+    table[b[0]:b[1]] = (torch.arange(b[0], b[1], dtype=torch.int32)[:, None] * 1000 + torch.arange(pitch, dtype=torch.int32)[None, :])
+    overflow = torch.tensor([1 if rank == 1 else 0], dtype=torch.int32)
+    exchange_codes(table, overflow, world, rank, dist)
+    want = torch.arange(rows, dtype=torch.int32)[:, None] * 1000 + torch.arange(pitch, dtype=torch.int32)[None, :]
+    q.put((rank, bool((table == want).all()), int(overflow[0]), b))
+    dist.destroy_process_group()
+
+
+def test_code_table_exchange_two_ranks():
+    # the one exchange step of the multi-rank MinHash path: each rank owns code_rows / world rows of the relabelled
+    # table, an in-place all-gather completes it and the overflow gate becomes the max over ranks
+    from dynaalign_b200.multirank import shard_bounds
+    assert shard_bounds(256, 1, 0) is None and shard_bounds(0, 2, 0) is None and shard_bounds(250, 4, 1) is None
+    assert [shard_bounds(256, 8, r) for r in (0, 7)] == [(0, 32), (224, 256)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_codes_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [(0, True, 1, (0, 8)), (1, True, 1, (8, 16))]
