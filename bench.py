@@ -460,7 +460,9 @@ def main():
         line = {
             "metric": "nw_allpairs_gcups", "value": nw_gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": nw_ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "s16x2", "data": "synthetic",
+            "dtype_note": "the reference's int32 DP evaluated exactly in packed 16-bit lanes (host range check per work unit; "
+                          "units that could leave int16 run the int32 kernels)",
             "config": {"workload": "similarityNW BLOSUM62 gapOpen=10 gapExt=4 on synthetic %d proteins of ~330 aa (BASELINE config 5), "
                                    "all %d pairs i<=j = %.4g DP cells per step; row blocks balanced by cells over %d rank(s)"
                                    % (n, int(total_pairs), total_cells, world),
