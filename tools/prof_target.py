@@ -1,4 +1,4 @@
-"""Development helper (GPU box): tiny single-shot workloads for ncu captures.  usage: prof_target.py nw|mh"""
+"""Development helper (GPU box): tiny single-shot workloads for ncu captures.  usage: prof_target.py nw|pep|mh [n]"""
 import ctypes as C
 import os
 import sys
@@ -11,9 +11,9 @@ from dynaalign_b200._lib import check, flatten, lib, ptr  # noqa: E402
 
 L = lib()
 what = sys.argv[1] if len(sys.argv) > 1 else "nw"
-if what == "nw":
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 700
-    seqs = synth.proteins_families(n)
+if what in ("nw", "pep"):
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else (700 if what == "nw" else 12000)
+    seqs = synth.proteins_families(n) if what == "nw" else synth.peptides_uniform(n)
     res, off = flatten(seqs)
     p = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, 0, n, 0)
     assert p, _lib.last_error()
