@@ -837,8 +837,10 @@ nw_thread_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units
 // here, so the 128-bit increment-table loads of VAR 2 cost four shared-memory wavefronts each and the kernel turns
 // shared-memory bound (measured 2.73 vs 3.09 TCUPS on 50,000 16-mers).
 // ------------------------------------------------------------------------------------------------
+// Strips up to 16 rows are held to 128 registers (4 CTAs per SM instead of 3; a few spilled words at R = 16):
+// measured 3.20 vs 3.09 TCUPS on 16-mers.  Taller strips keep the full register budget.
 template <int R>
-__global__ void __launch_bounds__(kThreadThreads)
+__global__ void __launch_bounds__(kThreadThreads, R <= 16 ? 4 : 1)
 nw_thread2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   using S = Strip<R>;
   __shared__ uint32_t prof[25 * S::RWS];  // class 24 = padding residue
