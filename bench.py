@@ -451,9 +451,12 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             tinfo = json.load(f)
-        # the committed ncu capture is of a REDUCED workload (tools/prof_target.py), so it is reported next to, not as,
-        # the per-launch traffic of this run
-        traffic = None
+        # profiles/traffic.json holds two captures: the dominant launch of the FULL config-5 workload on one GPU (dram bytes
+        # only) -- reported as `traffic` when this run is that workload -- and `ncu --set full` captures of a reduced
+        # workload (tools/prof_target.py), reported next to it
+        full = tinfo.get("nw_config5_dominant_launch")
+        if full and world == 1 and n == 20000:
+            traffic = full["dram_bytes"]
 
     if rank == 0:
         achieved = NW_OPS_PER_CELL * total_cells / (nw_ms_per_step * 1e-3) / world  # per GPU
@@ -474,6 +477,10 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "int32_issue", "achieved": achieved / 1e9, "peak": int_peak / 1e9, "unit": "Gop/s",
                          "frac": achieved / int_peak, "traffic": traffic,
+                         "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (nw_warp2_kernel<11>, "
+                                          "%.3g pairs of this workload), profiles/r01d_nw_config5_traffic.csv; algorithmic %.3g B"
+                                          % (tinfo["nw_config5_dominant_launch"]["pairs_upper_bound"],
+                                             tinfo["nw_config5_dominant_launch"]["algorithmic_bytes"])) if traffic else None,
                          "traffic_reduced_capture": {"dram_bytes": tinfo.get("nw_warp_kernel_dram_bytes_per_launch"),
                                                      "kernel": tinfo.get("nw_warp_kernel_dram_bytes_per_launch_kernel"),
                                                      "grid": tinfo.get("nw_warp_kernel_dram_bytes_per_launch_grid"),

@@ -63,8 +63,11 @@ for name in ("nw_prof", "mh_prof", "nw2_prof", "mh2_prof"):
 if traffic:
     traffic["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/prof_target.py: NW n=700 "
                        "families, MinHash n=32768 -> 536,854,528 pairs); the capture is a reduced workload, so bytes are per THAT launch")
-    with open(os.path.join(OUT, "traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    tp = os.path.join(OUT, "traffic.json")
+    merged = json.load(open(tp)) if os.path.exists(tp) else {}
+    merged.update(traffic)  # keep entries written by other captures (e.g. the full config-5 launch)
+    with open(tp, "w") as f:
+        json.dump(merged, f, indent=1)
 
 lp = os.path.join(G, "launches.csv")
 if os.path.exists(lp):
