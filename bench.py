@@ -505,7 +505,9 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": mh_alg_bytes / world / (mh_match_ms * 1e-3) / 1e9,
                              "peak": peaks_hbm(), "unit": "GB/s",
                              "frac": mh_alg_bytes / world / (mh_match_ms * 1e-3) / 1e9 / peaks_hbm(),
-                             "traffic": None,
+                             "traffic": (tinfo.get("mh_config4_match_launch", {}).get("dram_bytes")
+                                         if world == 1 and mn == 100000 else None),
+                             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the match launch at this workload (profiles/r01d_mh_config4_traffic.csv)",
                              "traffic_reduced_capture": {"dram_bytes": tinfo.get("mh_match_kernel_dram_bytes_per_launch"),
                                                          "algorithmic_bytes": 2.0 * 536854528 + 4.0 * 32768 * 500,
                                                          "note": "ncu --set full, MinHash n=32768 (536,854,528 pairs): measured DRAM bytes vs algorithmic"},
