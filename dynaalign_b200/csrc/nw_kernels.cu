@@ -424,6 +424,10 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   // results of one unit (<= 64 consecutive pair slots), written back as two coalesced 256-byte rows instead of one
   // 4-byte store per pair (ncu: the scattered stores cost 30 % extra DRAM write traffic plus read-modify-write reads)
   __shared__ uint32_t res_m[2 * kNwWarpUnitPairs], res_l[2 * kNwWarpUnitPairs];
+  // the unit's column sequences ordered by decreasing length: the two sequences that share a warp then differ by a
+  // residue or two instead of the ~11 of a random pairing (the shorter one idles for the difference)
+  __shared__ int col_len[2 * kNwWarpUnitPairs];
+  __shared__ uint8_t col_ord[2 * kNwWarpUnitPairs];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int go = d.gap_open, ge = d.gap_ext;
   const uint32_t ngo2 = pack16(-go);
@@ -442,6 +446,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int row = un.row;
     const int m = d.off[row + 1] - d.off[row];
     __syncthreads();
+    if (tid < un.j_count) col_len[tid] = d.off[un.j_begin + tid + 1] - d.off[un.j_begin + tid];
     build_profile<R, 32, L::kProfStride>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
     for (int idx = tid; idx < 32 * L::kProfStride; idx += THREADS) prof[24 * 32 * L::kProfStride + idx] = 0u;
     if (VAR == 2) {  // increment table: 1 | (row residue == class) << 16; padding rows and class 24 count steps only
@@ -455,6 +460,16 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       }
     }
     __syncthreads();
+    if (tid < un.j_count) {  // rank by (length descending, index ascending): a permutation of 0..j_count-1
+      const int mine = col_len[tid];
+      int rank = 0;
+      for (int q = 0; q < un.j_count; ++q) {
+        const int other = col_len[q];
+        rank += (other > mine || (other == mine && q < tid)) ? 1 : 0;
+      }
+      col_ord[rank] = (uint8_t)tid;
+    }
+    __syncthreads();
     const int lm = (m - 1) / R;
     const int km = (m - 1) - lm * R;
     const int r0 = lane * R;
@@ -464,10 +479,9 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const uint32_t* ilane = incT + lane * L::kIncStride;
 
     for (int pp = warp; pp < npairs2; pp += nwarps) {
-      int jA = un.j_begin + 2 * pp;
-      int jB = jA + 1;
-      const bool hasB = (jB < un.j_begin + un.j_count);
-      if (!hasB) jB = jA;
+      const bool hasB = (2 * pp + 1 < un.j_count);
+      int jA = un.j_begin + col_ord[2 * pp];
+      int jB = hasB ? un.j_begin + col_ord[2 * pp + 1] : jA;
       int nA = d.off[jA + 1] - d.off[jA], nB = d.off[jB + 1] - d.off[jB];
       if (nB > nA) {  // A is the longer column sequence
         int tj = jA; jA = jB; jB = tj;
