@@ -640,6 +640,8 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwMpStageCols + 8);
   const uint32_t* plane = prof + lane * L::kProfStride;
   const uint32_t* ilane = incT + lane * L::kIncStride;
+  __shared__ int col_len[2 * kNwMpPairSets];
+  __shared__ uint8_t col_ord[2 * kNwMpPairSets];
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
     const NwUnit un = units[u];
@@ -648,6 +650,20 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
     const uint8_t* __restrict__ a = d.codes + d.off[row];
     const int npass = (m + 32 * R - 1) / (32 * R);
     const int npairs2 = (un.j_count + 1) >> 1;
+    // column sequences paired by length, as in nw_warp2_kernel (long proteins differ by ~100 residues when paired at
+    // random); the order is fixed for the unit, so the per-pair-set scratch lines stay valid across passes
+    __syncthreads();
+    if (tid < un.j_count) col_len[tid] = d.off[un.j_begin + tid + 1] - d.off[un.j_begin + tid];
+    __syncthreads();
+    if (tid < un.j_count) {
+      const int mine = col_len[tid];
+      int rank = 0;
+      for (int q = 0; q < un.j_count; ++q) {
+        const int other = col_len[q];
+        rank += (other > mine || (other == mine && q < tid)) ? 1 : 0;
+      }
+      col_ord[rank] = (uint8_t)tid;
+    }
 
     for (int pass = 0; pass < npass; ++pass) {
       const int row0 = pass * 32 * R;
@@ -668,10 +684,9 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
       const int r0 = row0 + lane * R;
 
       for (int pp = warp; pp < npairs2; pp += nwarps) {
-        int jA = un.j_begin + 2 * pp;
-        int jB = jA + 1;
-        const bool hasB = (jB < un.j_begin + un.j_count);
-        if (!hasB) jB = jA;
+        const bool hasB = (2 * pp + 1 < un.j_count);
+        int jA = un.j_begin + col_ord[2 * pp];
+        int jB = hasB ? un.j_begin + col_ord[2 * pp + 1] : jA;
         int nA = d.off[jA + 1] - d.off[jA], nB = d.off[jB + 1] - d.off[jB];
         if (nB > nA) {
           int tj = jA; jA = jB; jB = tj;
