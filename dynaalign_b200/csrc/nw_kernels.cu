@@ -873,7 +873,8 @@ nw_thread_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units
 // as nw_warp2_kernel: a thread walks two column sequences against the CTA's row sequence, pair A in the low halves,
 // pair B in the high halves.  Stat increments stay on the PRMT form (VAR 1): every lane reads its own residue class
 // here, so the 128-bit increment-table loads of VAR 2 cost four shared-memory wavefronts each and the kernel turns
-// shared-memory bound (measured 2.73 vs 3.09 TCUPS on 50,000 16-mers).
+// shared-memory bound (measured 2.73 vs 3.09 TCUPS on 50,000 16-mers).  A single register set (the INPLACE form of
+// the warp kernel) at 96 registers / 5 CTAs per SM was also measured and dropped: 2.55 vs 3.20 TCUPS.
 // ------------------------------------------------------------------------------------------------
 // Strips up to 16 rows are held to 128 registers (4 CTAs per SM instead of 3; a few spilled words at R = 16):
 // measured 3.20 vs 3.09 TCUPS on 16-mers.  Taller strips keep the full register budget.
