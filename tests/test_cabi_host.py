@@ -145,3 +145,25 @@ def test_vocab_argument_errors_before_device():
     assert rc == _lib.ERR_INVALID and _lib.last_error() == "'k' must be a positive integer between 1 and 2"
     rc = lib().dyna_minhash_vocab_ranks(ptr(res, C2.c_uint8), ptr(off, C2.c_int64), 3, 0, None, 0, C2.byref(V), None, None)
     assert rc == _lib.ERR_INVALID and _lib.last_error() == "'k' must be a positive integer between 1 and 4"
+
+
+def test_fasta_reader(tmp_path):
+    import gzip
+
+    from dynaalign_b200.fasta import read_fasta
+    text = ">sp|P1 first protein\nARND\ncqeg\n\n>P2\nHILK MFPS*\n;comment\n>empty\n>P4\nTWYV\n"
+    p = tmp_path / "a.fasta"
+    p.write_text(text)
+    names, seqs = read_fasta(p)
+    assert names == ["sp|P1", "P2", "empty", "P4"]
+    assert seqs == ["ARNDCQEG", "HILKMFPS", "", "TWYV"]
+    assert read_fasta(p, upper=False, strip_terminator=False)[1][:2] == ["ARNDcqeg", "HILKMFPS*"]
+    gz = tmp_path / "a.fa.gz"
+    with gzip.open(gz, "wt") as f:
+        f.write(text)
+    assert read_fasta(gz) == (names, seqs)
+    bad = tmp_path / "bad.fa"
+    bad.write_text("ARND\n>x\nAA\n")
+    import pytest
+    with pytest.raises(ValueError):
+        read_fasta(bad)
