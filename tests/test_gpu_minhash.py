@@ -331,3 +331,17 @@ def test_relabelling_by_code_row_shards_equals_full(cuts, monkeypatch):
 def synth_peptides(n):
     from dynaalign_b200 import synth
     return synth.peptides_clustered(n, children=10)
+
+
+@pytest.mark.parametrize("pack16", ["0", "1"])
+def test_match_counts_several_tile_groups_and_slabs(pack16, monkeypatch):
+    # more than 64 tile rows: the grouped (L2-friendly) tile order walks several groups, also from a slab that starts
+    # in the middle of a group and of a tile
+    monkeypatch.setenv("DYNA_MH_PACK16", pack16)
+    rng = np.random.default_rng(21)
+    n, n_hash = 17000, 6
+    sig = rng.integers(0, 3, size=(n, n_hash), dtype=np.uint32)
+    for a, b in [(0, n), (4999, 13001), (16500, n)]:
+        want = port.mh_match_counts(sig, a, b)
+        got = da.mh_match_counts(sig, a, b)
+        assert len(got) == len(want) and (got == want).all(), (a, b)
