@@ -1,86 +1,73 @@
-// Routine registration for the DynaAlign shared object.  The first two entries are byte-for-byte the reference's
-// symbols and arities (_DynaAlign_similarityMH/3, _DynaAlign_similarityNW/4; its src/RcppExports.cpp:15,28,41-45),
-// so `useDynLib(DynaAlign, .registration = TRUE)` and the R stubs are unchanged.  Two internal entries serve the
-// GPU halves of the pure-R minhash() pipeline and one the sparse threshold step of clusterbreak.
+// Routine registration for the DynaAlign shared object, hand-written (not compileAttributes output).
+// The first two entry points keep the reference's symbols and arities -- _DynaAlign_similarityMH/3 and
+// _DynaAlign_similarityNW/4 (its src/RcppExports.cpp:15,28,41-45) -- so `useDynLib(DynaAlign, .registration = TRUE)`
+// and the R stubs keep working unchanged.  Three more serve this package's own R code: the GPU halves of the pure-R
+// minhash() pipeline and the sparse threshold step of clusterbreak.
 #include <Rcpp.h>
 
-using namespace Rcpp;
+#include <string>
 
+using Rcpp::CharacterVector;
+using Rcpp::IntegerMatrix;
+using Rcpp::IntegerVector;
+using Rcpp::NumericMatrix;
+using Rcpp::NumericVector;
+
+// implemented in dyna_shims.cpp
 NumericMatrix similarityMH(CharacterVector sequences, int k, int n_hash);
-RcppExport SEXP _DynaAlign_similarityMH(SEXP sequencesSEXP, SEXP kSEXP, SEXP n_hashSEXP) {
-BEGIN_RCPP
-    Rcpp::RObject rcpp_result_gen;
-    Rcpp::RNGScope rcpp_rngScope_gen;
-    Rcpp::traits::input_parameter< CharacterVector >::type sequences(sequencesSEXP);
-    Rcpp::traits::input_parameter< int >::type k(kSEXP);
-    Rcpp::traits::input_parameter< int >::type n_hash(n_hashSEXP);
-    rcpp_result_gen = Rcpp::wrap(similarityMH(sequences, k, n_hash));
-    return rcpp_result_gen;
-END_RCPP
-}
-
 NumericMatrix similarityNW(CharacterVector sequences, std::string matrixName, int gapOpen, int gapExt);
-RcppExport SEXP _DynaAlign_similarityNW(SEXP sequencesSEXP, SEXP matrixNameSEXP, SEXP gapOpenSEXP, SEXP gapExtSEXP) {
-BEGIN_RCPP
-    Rcpp::RObject rcpp_result_gen;
-    Rcpp::RNGScope rcpp_rngScope_gen;
-    Rcpp::traits::input_parameter< CharacterVector >::type sequences(sequencesSEXP);
-    Rcpp::traits::input_parameter< std::string >::type matrixName(matrixNameSEXP);
-    Rcpp::traits::input_parameter< int >::type gapOpen(gapOpenSEXP);
-    Rcpp::traits::input_parameter< int >::type gapExt(gapExtSEXP);
-    rcpp_result_gen = Rcpp::wrap(similarityNW(sequences, matrixName, gapOpen, gapExt));
-    return rcpp_result_gen;
-END_RCPP
-}
-
-NumericMatrix mh_signatures_linear(IntegerVector ranks, NumericVector offsets, NumericVector a, NumericVector b, double m, int n_hash);
-RcppExport SEXP _DynaAlign_mh_signatures_linear(SEXP ranksSEXP, SEXP offsetsSEXP, SEXP aSEXP, SEXP bSEXP, SEXP mSEXP, SEXP n_hashSEXP) {
-BEGIN_RCPP
-    Rcpp::RObject rcpp_result_gen;
-    Rcpp::traits::input_parameter< IntegerVector >::type ranks(ranksSEXP);
-    Rcpp::traits::input_parameter< NumericVector >::type offsets(offsetsSEXP);
-    Rcpp::traits::input_parameter< NumericVector >::type a(aSEXP);
-    Rcpp::traits::input_parameter< NumericVector >::type b(bSEXP);
-    Rcpp::traits::input_parameter< double >::type m(mSEXP);
-    Rcpp::traits::input_parameter< int >::type n_hash(n_hashSEXP);
-    rcpp_result_gen = Rcpp::wrap(mh_signatures_linear(ranks, offsets, a, b, m, n_hash));
-    return rcpp_result_gen;
-END_RCPP
-}
-
-NumericMatrix mh_distance_matrix(IntegerMatrix codes);
-RcppExport SEXP _DynaAlign_mh_distance_matrix(SEXP codesSEXP) {
-BEGIN_RCPP
-    Rcpp::RObject rcpp_result_gen;
-    Rcpp::traits::input_parameter< IntegerMatrix >::type codes(codesSEXP);
-    rcpp_result_gen = Rcpp::wrap(mh_distance_matrix(codes));
-    return rcpp_result_gen;
-END_RCPP
-}
-
 NumericMatrix similarityMH_edges(CharacterVector sequences, int k, int n_hash, double thresh_p);
-RcppExport SEXP _DynaAlign_similarityMH_edges(SEXP sequencesSEXP, SEXP kSEXP, SEXP n_hashSEXP, SEXP thresh_pSEXP) {
-BEGIN_RCPP
-    Rcpp::RObject rcpp_result_gen;
-    Rcpp::traits::input_parameter< CharacterVector >::type sequences(sequencesSEXP);
-    Rcpp::traits::input_parameter< int >::type k(kSEXP);
-    Rcpp::traits::input_parameter< int >::type n_hash(n_hashSEXP);
-    Rcpp::traits::input_parameter< double >::type thresh_p(thresh_pSEXP);
-    rcpp_result_gen = Rcpp::wrap(similarityMH_edges(sequences, k, n_hash, thresh_p));
-    return rcpp_result_gen;
-END_RCPP
+NumericMatrix mh_signatures_linear(IntegerVector ranks, NumericVector offsets, NumericVector a, NumericVector b, double m,
+                                   int n_hash);
+NumericMatrix mh_distance_matrix(IntegerMatrix codes);
+
+// BEGIN_RCPP / END_RCPP turn C++ exceptions (Rcpp::stop in the shims) into R errors, as in the reference's wrappers;
+// an RNGScope is held for the two reference entry points because the reference's wrappers hold one as well.
+RcppExport SEXP _DynaAlign_similarityMH(SEXP seqs, SEXP k, SEXP nHash) {
+  BEGIN_RCPP
+  Rcpp::RNGScope rng;
+  return Rcpp::wrap(similarityMH(Rcpp::as<CharacterVector>(seqs), Rcpp::as<int>(k), Rcpp::as<int>(nHash)));
+  END_RCPP
 }
 
-static const R_CallMethodDef CallEntries[] = {
-    {"_DynaAlign_similarityMH", (DL_FUNC) &_DynaAlign_similarityMH, 3},
-    {"_DynaAlign_similarityNW", (DL_FUNC) &_DynaAlign_similarityNW, 4},
-    {"_DynaAlign_mh_signatures_linear", (DL_FUNC) &_DynaAlign_mh_signatures_linear, 6},
-    {"_DynaAlign_mh_distance_matrix", (DL_FUNC) &_DynaAlign_mh_distance_matrix, 1},
-    {"_DynaAlign_similarityMH_edges", (DL_FUNC) &_DynaAlign_similarityMH_edges, 4},
-    {NULL, NULL, 0}
-};
+RcppExport SEXP _DynaAlign_similarityNW(SEXP seqs, SEXP table, SEXP open, SEXP ext) {
+  BEGIN_RCPP
+  Rcpp::RNGScope rng;
+  return Rcpp::wrap(similarityNW(Rcpp::as<CharacterVector>(seqs), Rcpp::as<std::string>(table), Rcpp::as<int>(open),
+                                 Rcpp::as<int>(ext)));
+  END_RCPP
+}
 
-RcppExport void R_init_DynaAlign(DllInfo *dll) {
-    R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
-    R_useDynamicSymbols(dll, FALSE);
+RcppExport SEXP _DynaAlign_similarityMH_edges(SEXP seqs, SEXP k, SEXP nHash, SEXP p) {
+  BEGIN_RCPP
+  return Rcpp::wrap(similarityMH_edges(Rcpp::as<CharacterVector>(seqs), Rcpp::as<int>(k), Rcpp::as<int>(nHash),
+                                       Rcpp::as<double>(p)));
+  END_RCPP
+}
+
+RcppExport SEXP _DynaAlign_mh_signatures_linear(SEXP ranks, SEXP offsets, SEXP a, SEXP b, SEXP m, SEXP nHash) {
+  BEGIN_RCPP
+  return Rcpp::wrap(mh_signatures_linear(Rcpp::as<IntegerVector>(ranks), Rcpp::as<NumericVector>(offsets),
+                                         Rcpp::as<NumericVector>(a), Rcpp::as<NumericVector>(b), Rcpp::as<double>(m),
+                                         Rcpp::as<int>(nHash)));
+  END_RCPP
+}
+
+RcppExport SEXP _DynaAlign_mh_distance_matrix(SEXP codes) {
+  BEGIN_RCPP
+  return Rcpp::wrap(mh_distance_matrix(Rcpp::as<IntegerMatrix>(codes)));
+  END_RCPP
+}
+
+static const R_CallMethodDef kCallEntries[] = {
+    {"_DynaAlign_similarityMH", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityMH), 3},
+    {"_DynaAlign_similarityNW", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityNW), 4},
+    {"_DynaAlign_similarityMH_edges", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityMH_edges), 4},
+    {"_DynaAlign_mh_signatures_linear", reinterpret_cast<DL_FUNC>(&_DynaAlign_mh_signatures_linear), 6},
+    {"_DynaAlign_mh_distance_matrix", reinterpret_cast<DL_FUNC>(&_DynaAlign_mh_distance_matrix), 1},
+    {nullptr, nullptr, 0}};
+
+RcppExport void R_init_DynaAlign(DllInfo* dll) {
+  R_registerRoutines(dll, nullptr, kCallEntries, nullptr, nullptr);
+  R_useDynamicSymbols(dll, FALSE);
 }
