@@ -34,6 +34,8 @@
 //                           profile reads are bank-conflict free (distinct residue class -> distinct bank).
 #include "nw_kernels.cuh"
 
+#include <type_traits>
+
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -518,6 +520,11 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       const unsigned n_act = (lane <= lm) ? (unsigned)nA : 0u;  // columns this lane processes
       const int capB = (lane == lm) ? nB - 1 : -1;              // column at which pair B's result is final
       const int T = nA + lm;
+      // the step loop exists twice, specialised on ROT (warp-uniform): with the rotation the border row costs nothing,
+      // without it lane 0 overrides four registers per step -- selects that would otherwise sit on the ALU pipe of
+      // every step of every unit
+      auto run_steps = [&](auto rot_c) {
+      constexpr bool ROT = decltype(rot_c)::value;
       for (int t0 = 0; t0 < T; t0 += 2) {
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
@@ -526,7 +533,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
           uint32_t rF = __shfl_sync(full, outF, src_lane);
           uint32_t rSA = __shfl_sync(full, outSA, src_lane);
           uint32_t rSB = __shfl_sync(full, outSB, src_lane);
-          if (!rot) {  // all 32 lanes own rows: lane 0 takes the border row explicitly
+          if (!ROT) {  // all 32 lanes own rows: lane 0 takes the border row explicitly
             if (lane == 0) {
               rH = bord2;
               rF = sent2;
@@ -577,6 +584,9 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
           }
         }
       }
+      };
+      if (rot) run_steps(std::true_type{});
+      else run_steps(std::false_type{});
       const bool in1 = (((lm + nA) & 1) != 0);
       uint32_t resA = 0u;
 #pragma unroll
