@@ -324,14 +324,32 @@ struct Stat2Consts {
   uint32_t one, zero;
 };
 
+// Shared-memory loads through explicit 32-bit shared-window addresses (the generic-pointer form made ptxas rebuild
+// the window base with four uniform-datapath instructions in every step of the hot loop).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 template <int R, int VAR>
 __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
                                               const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
                                               uint32_t (&SBn)[R], const uint32_t (&pwA)[Strip<R>::RW],
                                               const uint32_t (&pwB)[Strip<R>::RW], uint32_t diagH, uint32_t dSA,
                                               uint32_t dSB, uint32_t F, uint32_t upSA, uint32_t upSB, uint32_t ngo2,
-                                              const Stat2Consts& c, uint32_t& outF, const uint4* __restrict__ incA4 = nullptr,
-                                              const uint4* __restrict__ incB4 = nullptr) {
+                                              const Stat2Consts& c, uint32_t& outF, uint32_t incA_sh = 0u,
+                                              uint32_t incB_sh = 0u) {
   // VAR 2: the stat increments (1 | eq << 16) are read ready-made from a shared-memory table, four rows per 128-bit
   // load, instead of being permuted out of the profile word: two fewer ALU-pipe instructions per two cells
   uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
@@ -342,8 +360,8 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
     uint32_t incA, incB;
     if (VAR == 2) {
       if ((k & 3) == 0) {
-        qa = incA4[k >> 2];
-        qb = incB4[k >> 2];
+        qa = lds_v4(incA_sh + 4u * (unsigned)k);  // rows k..k+3 (constant offset after unrolling)
+        qb = lds_v4(incB_sh + 4u * (unsigned)k);
       }
       incA = (k & 3) == 0 ? qa.x : (k & 3) == 1 ? qa.y : (k & 3) == 2 ? qa.z : qa.w;
       incB = (k & 3) == 0 ? qb.x : (k & 3) == 1 ? qb.y : (k & 3) == 2 ? qb.z : qb.w;
@@ -442,6 +460,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   const int src_lane = (lane + 31) & 31;  // rotating "shuffle up": lane 0 reads lane 31
   uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwStageCols + 8);
   uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwStageCols + 8);
+  const uint32_t sA_sh = (uint32_t)__cvta_generic_to_shared(sA), sB_sh = (uint32_t)__cvta_generic_to_shared(sB);
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
     const NwUnit un = units[u];
@@ -477,8 +496,8 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int r0 = lane * R;
     const bool rot = (lm < 31);  // lane 31 idle: it can hold the border row for lane 0
     const int npairs2 = (un.j_count + 1) >> 1;
-    const uint32_t* plane = prof + lane * L::kProfStride;
-    const uint32_t* ilane = incT + lane * L::kIncStride;
+    const uint32_t plane_sh = (uint32_t)__cvta_generic_to_shared(prof + lane * L::kProfStride);
+    const uint32_t ilane_sh = (uint32_t)__cvta_generic_to_shared(incT + lane * L::kIncStride);
 
     for (int pp = warp; pp < npairs2; pp += nwarps) {
       const bool hasB = (2 * pp + 1 < un.j_count);
@@ -515,7 +534,10 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
       uint32_t prevUpSA = 0u, prevUpSB = 0u;
       // lane 31 (idle when rot) carries the border row: H_diag = -go+ge (slanted), F = sentinel, stats 0
-      uint32_t outH = bord2, outF = sent2, outSA = 0u, outSB = 0u;
+      // what the lane below reads is always the bottom row written in the previous step, i.e. H/SA/SB[R-1] of the set
+      // this phase reads -- shuffled straight out of the strip registers (no copies); only F needs its own register.
+      // An idle lane 31 never writes its strip, so it keeps offering the border constants it was initialised with.
+      uint32_t outF = sent2;
       uint32_t resB = 0u;
       const unsigned n_act = (lane <= lm) ? (unsigned)nA : 0u;  // columns this lane processes
       const int capB = (lane == lm) ? nB - 1 : -1;              // column at which pair B's result is final
@@ -529,10 +551,11 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
           const int jc = t0 + ph - lane;
-          uint32_t rH = __shfl_sync(full, outH, src_lane);
+          const bool from1 = !INPLACE && ph == 1;  // the register set the previous step wrote
+          uint32_t rH = __shfl_sync(full, from1 ? H1[INPLACE ? 0 : R - 1] : H0[R - 1], src_lane);
           uint32_t rF = __shfl_sync(full, outF, src_lane);
-          uint32_t rSA = __shfl_sync(full, outSA, src_lane);
-          uint32_t rSB = __shfl_sync(full, outSB, src_lane);
+          uint32_t rSA = __shfl_sync(full, from1 ? SA1[INPLACE ? 0 : R - 1] : SA0[R - 1], src_lane);
+          uint32_t rSB = __shfl_sync(full, from1 ? SB1[INPLACE ? 0 : R - 1] : SB0[R - 1], src_lane);
           if (!ROT) {  // all 32 lanes own rows: lane 0 takes the border row explicitly
             if (lane == 0) {
               rH = bord2;
@@ -542,36 +565,26 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
             }
           }
           if ((unsigned)jc < n_act) {
-            const int cA = sA[jc];
-            const int cB = sB[jc];
+            const uint32_t cA = lds_u8(sA_sh + (uint32_t)jc), cB = lds_u8(sB_sh + (uint32_t)jc);
             uint32_t pwA[S::RW], pwB[S::RW];
-            const uint32_t* pa = plane + cA * (32 * L::kProfStride);
-            const uint32_t* pb = plane + cB * (32 * L::kProfStride);
-            const uint4* ia = reinterpret_cast<const uint4*>(ilane + cA * (32 * L::kIncStride));
-            const uint4* ib = reinterpret_cast<const uint4*>(ilane + cB * (32 * L::kIncStride));
+            const uint32_t pa = plane_sh + cA * (32u * L::kProfStride * 4u);
+            const uint32_t pb = plane_sh + cB * (32u * L::kProfStride * 4u);
+            const uint32_t ia = ilane_sh + cA * (32u * L::kIncStride * 4u);
+            const uint32_t ib = ilane_sh + cB * (32u * L::kIncStride * 4u);
 #pragma unroll
             for (int w = 0; w < S::RW; ++w) {
-              pwA[w] = pa[w];
-              pwB[w] = pb[w];
+              pwA[w] = lds_u32(pa + 4u * (unsigned)w);
+              pwB[w] = lds_u32(pb + 4u * (unsigned)w);
             }
             if constexpr (INPLACE) {
               strip_column2<R, VAR>(H0, H0, El, SA0, SA0, SB0, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
                                     ngo2, c, outF, ia, ib);
-              outH = H0[R - 1];
-              outSA = SA0[R - 1];
-              outSB = SB0[R - 1];
             } else if (ph == 0) {
               strip_column2<R, VAR>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
                                     ngo2, c, outF, ia, ib);
-              outH = H1[R - 1];
-              outSA = SA1[R - 1];
-              outSB = SB1[R - 1];
             } else {
               strip_column2<R, VAR>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
                                     ngo2, c, outF, ia, ib);
-              outH = H0[R - 1];
-              outSA = SA0[R - 1];
-              outSB = SB0[R - 1];
             }
             prevUpH = rH;
             prevUpSA = rSA;
@@ -649,7 +662,7 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwMpStageCols + 8);
   uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwMpStageCols + 8);
   const uint32_t* plane = prof + lane * L::kProfStride;
-  const uint32_t* ilane = incT + lane * L::kIncStride;
+  const uint32_t ilane_sh = (uint32_t)__cvta_generic_to_shared(incT + lane * L::kIncStride);
   __shared__ int col_len[2 * kNwMpPairSets];
   __shared__ uint8_t col_ord[2 * kNwMpPairSets];
 
@@ -753,8 +766,8 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
               uint32_t pwA[S::RW], pwB[S::RW];
               const uint32_t* pa = plane + cA * (32 * L::kProfStride);
               const uint32_t* pb = plane + cB * (32 * L::kProfStride);
-              const uint4* ia = reinterpret_cast<const uint4*>(ilane + cA * (32 * L::kIncStride));
-              const uint4* ib = reinterpret_cast<const uint4*>(ilane + cB * (32 * L::kIncStride));
+              const uint32_t ia = ilane_sh + (uint32_t)cA * (32u * L::kIncStride * 4u);
+              const uint32_t ib = ilane_sh + (uint32_t)cB * (32u * L::kIncStride * 4u);
 #pragma unroll
               for (int w = 0; w < S::RW; ++w) {
                 pwA[w] = pa[w];
