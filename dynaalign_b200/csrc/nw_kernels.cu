@@ -661,7 +661,8 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   const unsigned full = 0xFFFFFFFFu;
   uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwMpStageCols + 8);
   uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwMpStageCols + 8);
-  const uint32_t* plane = prof + lane * L::kProfStride;
+  const uint32_t sA_sh = (uint32_t)__cvta_generic_to_shared(sA), sB_sh = (uint32_t)__cvta_generic_to_shared(sB);
+  const uint32_t plane_sh = (uint32_t)__cvta_generic_to_shared(prof + lane * L::kProfStride);
   const uint32_t ilane_sh = (uint32_t)__cvta_generic_to_shared(incT + lane * L::kIncStride);
   __shared__ int col_len[2 * kNwMpPairSets];
   __shared__ uint8_t col_ord[2 * kNwMpPairSets];
@@ -761,17 +762,16 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
               if (from_scr && jc + 1 < nA) nxt = scr[jc + 1];
             }
             if ((unsigned)jc < n_act) {
-              const int cA = sA[jc];
-              const int cB = sB[jc];
+              const uint32_t cA = lds_u8(sA_sh + (uint32_t)jc), cB = lds_u8(sB_sh + (uint32_t)jc);
               uint32_t pwA[S::RW], pwB[S::RW];
-              const uint32_t* pa = plane + cA * (32 * L::kProfStride);
-              const uint32_t* pb = plane + cB * (32 * L::kProfStride);
-              const uint32_t ia = ilane_sh + (uint32_t)cA * (32u * L::kIncStride * 4u);
-              const uint32_t ib = ilane_sh + (uint32_t)cB * (32u * L::kIncStride * 4u);
+              const uint32_t pa = plane_sh + cA * (32u * L::kProfStride * 4u);
+              const uint32_t pb = plane_sh + cB * (32u * L::kProfStride * 4u);
+              const uint32_t ia = ilane_sh + cA * (32u * L::kIncStride * 4u);
+              const uint32_t ib = ilane_sh + cB * (32u * L::kIncStride * 4u);
 #pragma unroll
               for (int w = 0; w < S::RW; ++w) {
-                pwA[w] = pa[w];
-                pwB[w] = pb[w];
+                pwA[w] = lds_u32(pa + 4u * (unsigned)w);
+                pwB[w] = lds_u32(pb + 4u * (unsigned)w);
               }
               if (ph == 0) {
                 strip_column2<R, 2>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
