@@ -1042,7 +1042,8 @@ template <int R>
 int launch_warp2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   // measured on B200 (TCUPS, config 5 / config 2):
   //   strips R <= 12: ping-pong register sets, 8-warp CTAs, increments from the shared-memory table (VAR 2): 2.94
-  //                   (VAR 1, increments by PRMT: 2.72 on the same box; one register set: 2.58)
+  //                   (VAR 1, increments by PRMT: 2.72 on the same box; one register set: 2.58; with the final step
+  //                   loop: table for all rows 3.17, for the first 8 rows 3.12, first 4 rows 3.08, PRMT only 3.00)
   //   strips R >= 13: one register set, 4-warp CTAs, increments by PRMT (VAR 1): 2.60 (VAR 2: 2.48; ping-pong: 2.27;
   //                   VAR 2 with one register set in 8-warp CTAs at 128 registers, 16 warps/SM, R <= 18: 2.56)
   if constexpr (R >= 13) return launch_warp2_inst<R, 1, true, 128>(d, d_units, num_units, st);
