@@ -302,6 +302,9 @@ __device__ __forceinline__ void count_eq(uint32_t& cnt, uint32_t a, uint32_t b) 
   asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(cnt) : "r"(a), "r"(b));
 }
 
+// `lim` < kMatchBK only for the last stage of a hash dimension that is not a multiple of kMatchBK: the rows beyond it
+// are layout padding (zeros) and are skipped instead of being counted and subtracted again.
+__device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty, int tx, uint32_t (&cnt)[8][8], int lim);
 __device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty, int tx, uint32_t (&cnt)[8][8]) {
 #pragma unroll
   for (int hh = 0; hh < kMatchBK; ++hh) {
@@ -334,6 +337,40 @@ __device__ __forceinline__ void match_stage_compute16(const MatchStage& st, int 
                                                       uint32_t minus1) {
 #pragma unroll
   for (int hh = 0; hh < kMatchBK; ++hh) {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh][ty * 4]);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh][64 + ty * 4]);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh][tx * 4]);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(&st.b[hh][64 + tx * 4]);
+    const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) count_eq2(acc[i][j], av[i], bv[j], minus1);
+  }
+}
+
+__device__ __forceinline__ void match_stage_compute(const MatchStage& st, int ty, int tx, uint32_t (&cnt)[8][8], int lim) {
+#pragma unroll
+  for (int hh = 0; hh < kMatchBK; ++hh) {
+    if (hh >= lim) break;  // warp-uniform; the rows stay fully unrolled with constant shared-memory offsets
+    const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh][ty * 4]);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh][64 + ty * 4]);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh][tx * 4]);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(&st.b[hh][64 + tx * 4]);
+    const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) count_eq(cnt[i][j], av[i], bv[j]);
+  }
+}
+__device__ __forceinline__ void match_stage_compute16(const MatchStage& st, int ty, int tx, uint32_t (&acc)[8][8],
+                                                      uint32_t minus1, int lim) {
+#pragma unroll
+  for (int hh = 0; hh < kMatchBK; ++hh) {
+    if (hh >= lim) break;  // warp-uniform; the rows stay fully unrolled with constant shared-memory offsets
     const uint4 a0 = *reinterpret_cast<const uint4*>(&st.a[hh][ty * 4]);
     const uint4 a1 = *reinterpret_cast<const uint4*>(&st.a[hh][64 + ty * 4]);
     const uint4 b0 = *reinterpret_cast<const uint4*>(&st.b[hh][tx * 4]);
@@ -434,7 +471,7 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int rows, int pad, int6
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int lx = tid & 31, lw = tid >> 5;
-  const int nkb = rows / kMatchBK;
+  const int nkb = (rows + kMatchBK - 1) / kMatchBK;  // `rows` = rows that carry data; the last box may be partly padding
 
   if (tid == 0) {
     for (int s = 0; s < kMatchStages; ++s) mbar_init(&full[s], 1);
@@ -466,13 +503,22 @@ mh_match_tma_kernel(const __grid_constant__ TmapPair tm, int rows, int pad, int6
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       for (int p = 0; p < kMatchStages - 1 && p < nkb; ++p) issue(p, (it + p) % kMatchStages);
     }
-    for (int kb = 0; kb < nkb; ++kb, ++it) {
+    const int nfull = rows / kMatchBK;  // stages whose 16 rows all carry data; at most one partial stage follows
+    for (int kb = 0; kb < nfull; ++kb, ++it) {
       const uint32_t slot = it % kMatchStages;
       if (tid == 0 && kb + kMatchStages - 1 < nkb) issue(kb + kMatchStages - 1, (it + kMatchStages - 1) % kMatchStages);
       mbar_wait(&full[slot], (it / kMatchStages) & 1u);
       if (PAIRS16) match_stage_compute16(stages[slot], ty, tx, ne, minus1);
       else match_stage_compute(stages[slot], ty, tx, ne);
       __syncthreads();  // slot free for the load issued at the top of the next iteration
+    }
+    if (nfull < nkb) {  // the partial stage is peeled so that the loop above keeps its register allocation and schedule
+      const uint32_t slot = it % kMatchStages;
+      mbar_wait(&full[slot], (it / kMatchStages) & 1u);
+      if (PAIRS16) match_stage_compute16(stages[slot], ty, tx, ne, minus1, rows - nfull * kMatchBK);
+      else match_stage_compute(stages[slot], ty, tx, ne, rows - nfull * kMatchBK);
+      __syncthreads();
+      ++it;
     }
     if (PAIRS16) {
 #pragma unroll
@@ -899,16 +945,17 @@ int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_has
   int nl = 0;
   if (d_sigP) {
     // 16-bit codes, two hash components per word; runs only if the relabelling did not overflow
-    const int rows2 = mh_hrows2(n_hash);
+    const int rows2 = mh_hrows2(n_hash);       // rows of the layout (a multiple of kMatchBK)
+    const int used2 = (n_hash + 1) / 2;        // rows that carry codes; an odd n_hash leaves one padding half-word
     DYNA_TRY(encode_sig_tmap(tm.a, d_sigP, npitch, rows2));
-    mh_match_tma_kernel<true><<<grid, kMatchThreads, smem, st>>>(tm, rows2, 2 * rows2 - n_hash, n, tile_base, row_begin,
+    mh_match_tma_kernel<true><<<grid, kMatchThreads, smem, st>>>(tm, used2, 2 * used2 - n_hash, n, tile_base, row_begin,
                                                                  row_end, d_counts, slab_base, T0, NA, num_tiles, d_overflow, 0);
     DYNA_CUDA(cudaGetLastError());
     ++nl;
   }
   // 32-bit signatures: always when there is no 16-bit copy, otherwise only if the relabelling overflowed
   DYNA_TRY(encode_sig_tmap(tm.a, d_sigT, npitch, hrows));
-  mh_match_tma_kernel<false><<<grid, kMatchThreads, smem, st>>>(tm, hrows, hrows - n_hash, n, tile_base, row_begin, row_end,
+  mh_match_tma_kernel<false><<<grid, kMatchThreads, smem, st>>>(tm, n_hash, 0, n, tile_base, row_begin, row_end,
                                                                 d_counts, slab_base, T0, NA, num_tiles,
                                                                 d_sigP ? d_overflow : nullptr, 1);
   DYNA_CUDA(cudaGetLastError());
