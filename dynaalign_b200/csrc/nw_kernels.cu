@@ -736,7 +736,7 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
         }
         uint32_t prevUpH = (r0 == 0) ? 0u : bord2;  // diagonal source (r0, 0): corner only for the very first row
         uint32_t prevUpSA = 0u, prevUpSB = 0u;
-        uint32_t outH = 0u, outF = 0u, outSA = 0u, outSB = 0u;
+        uint32_t outF = 0u;  // H and the stats of the bottom row are shuffled straight out of the strip registers
         uint32_t resB = 0u;
         const unsigned n_act = (lane <= lm) ? (unsigned)nA : 0u;
         const int capB = (last_pass && lane == lm) ? nB - 1 : -1;
@@ -750,10 +750,11 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {
             const int jc = t0 + ph - lane;
-            uint32_t rH = __shfl_up_sync(full, outH, 1);
+            // the previous step wrote the register set this phase reads
+            uint32_t rH = __shfl_up_sync(full, ph == 1 ? H1[R - 1] : H0[R - 1], 1);
             uint32_t rF = __shfl_up_sync(full, outF, 1);
-            uint32_t rSA = __shfl_up_sync(full, outSA, 1);
-            uint32_t rSB = __shfl_up_sync(full, outSB, 1);
+            uint32_t rSA = __shfl_up_sync(full, ph == 1 ? SA1[R - 1] : SA0[R - 1], 1);
+            uint32_t rSB = __shfl_up_sync(full, ph == 1 ? SB1[R - 1] : SB0[R - 1], 1);
             if (lane == 0) {  // pass 0: border row (nxt stays at the border constants); later passes: scratch
               rH = nxt.x;
               rF = nxt.y;
@@ -776,20 +777,16 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
               if (ph == 0) {
                 strip_column2<R, 2>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
                                     ngo2, c, outF, ia, ib);
-                outH = H1[R - 1];
-                outSA = SA1[R - 1];
-                outSB = SB1[R - 1];
               } else {
                 strip_column2<R, 2>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
                                     ngo2, c, outF, ia, ib);
-                outH = H0[R - 1];
-                outSA = SA0[R - 1];
-                outSB = SB0[R - 1];
               }
               prevUpH = rH;
               prevUpSA = rSA;
               prevUpSB = rSB;
-              if (!last_pass && lane == 31) scr[jc] = make_uint4(outH, outF, outSA, outSB);
+              if (!last_pass && lane == 31)  // the bottom row just written (the other register set)
+                scr[jc] = ph == 0 ? make_uint4(H1[R - 1], outF, SA1[R - 1], SB1[R - 1])
+                                  : make_uint4(H0[R - 1], outF, SA0[R - 1], SB0[R - 1]);
               if (jc == capB) {
 #pragma unroll
                 for (int k = 0; k < R; ++k)
