@@ -443,7 +443,7 @@ def main():
     # ================================================================== BASELINE configs 1-3 through the drop-in API (rank 0)
     other = None
     if rank == 0:
-        other = small_configs(dev)
+        other = small_configs(dev, with_cpu=(world == 1 and not args.skip_cpu))
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -526,7 +526,7 @@ def main():
         dist.destroy_process_group()
 
 
-def small_configs(dev):
+def small_configs(dev, with_cpu=False):
     """BASELINE configs 1, 2 and the sim_fn of config 3 on the reference's own data (fixtures under tests/golden),
     end to end through the drop-in entry points: host strings in, host n x n double matrix out."""
     import gzip
@@ -558,6 +558,11 @@ def small_configs(dev):
     cells = int((lens * np.cumsum(lens[::-1])[::-1]).sum())
     t = best_of(lambda: da.similarityNW(h3))
     out["config2_similarityNW_h3n2_1000"] = {"n": len(h3), "cells": cells, "seconds": t, "gcups": cells / t / 1e9}
+    if with_cpu:  # the reference on a bounded sample of the same input (first 32 sequences), 1 core
+        gc, dt, ccells, kind = cpu_nw_sample(h3, 32)
+        out["config2_similarityNW_h3n2_1000"]["cpu_baseline"] = {
+            "value": gc, "unit": "GCUPS", "cores": 1, "kind": kind,
+            "sample": "reference similarityNW on h3n2sample[1:32] (%d cells, %.1f s)" % (ccells, dt)}
     t = best_of(lambda: da.similarityMH(h3, 4, 500, seed=42))
     out["config3_simfn_similarityMH_h3n2_1000_k4_h500"] = {"n": len(h3), "seconds": t,
                                                             "pairs_per_s": len(h3) * (len(h3) - 1) / 2 / t}
