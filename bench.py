@@ -439,6 +439,9 @@ def main():
         rate, dt, pairs, kind = cpu_mh_sample(peps, 12000, cores)
         cpu_mh = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
                   "sample": "reference similarityMH on the first 12000 peptides of config 4 (%d pairs, %.1f s), OpenMP on all host cores" % (pairs, dt)}
+        rate1, dt1, pairs1, _ = cpu_mh_sample(peps, 4000, 1)
+        cpu_mh["one_core"] = {"value": rate1, "unit": "pairs/s", "cores": 1,
+                              "sample": "first 4000 peptides (%d pairs, %.1f s), OMP_NUM_THREADS=1" % (pairs1, dt1)}
 
     # ================================================================== BASELINE configs 1-3 through the drop-in API (rank 0)
     other = None
