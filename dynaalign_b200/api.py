@@ -24,7 +24,7 @@ from ._lib import DynaAlignError, check, flatten, lib, ptr
 __all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
            "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
            "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
-           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError"]
+           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "NWPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError"]
 
 
 def dimnames(n):
@@ -259,6 +259,44 @@ class MinHashPlan:
         if not h:
             raise DynaAlignError(L.ERR_INVALID, L.last_error())
         return MinHashPlan(n_hash=self.n_hash, _handle=h, _n=len(idx))
+
+
+class NWPlan:
+    """Device-resident Needleman-Wunsch state for one set of sequences and one row range: validate, encode and build
+    the work units once, then run (and re-run) the kernels and fetch the (matches, length) slab when wanted."""
+
+    def __init__(self, sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, row_begin=0, row_end=None, device=0):
+        sequences = list(sequences)
+        self.n = len(sequences)
+        self.row_begin, self.row_end = int(row_begin), self.n if row_end is None else int(row_end)
+        res, off = flatten(sequences)
+        self._h = lib().dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), self.n, matrixName.encode(), int(gapOpen),
+                                            int(gapExt), self.row_begin, self.row_end, int(device))
+        if not self._h:
+            msg = L.last_error()
+            raise DynaAlignError(L.ERR_CUDA if msg.startswith("DynaAlign CUDA") else L.ERR_INVALID, msg)
+
+    pairs = property(lambda self: lib().dyna_nw_plan_pairs(self._h))
+    cells = property(lambda self: lib().dyna_nw_plan_cells(self._h))
+
+    def run(self, stream=None):
+        check(lib().dyna_nw_plan_run(self._h, stream))
+        return self
+
+    def fetch(self):
+        """(matches, length) of the plan's pairs, packed upper triangle (diagonal included), row-major."""
+        sz = self.pairs
+        mt = np.zeros(max(sz, 1), dtype=np.uint32)
+        ln = np.zeros(max(sz, 1), dtype=np.uint32)
+        check(lib().dyna_nw_plan_fetch(self._h, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32), None))
+        return mt[:sz], ln[:sz]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dyna_nw_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 # ----------------------------------------------------------------------------- R pipeline (R/minHash.R)

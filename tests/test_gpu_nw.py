@@ -219,3 +219,21 @@ def test_int16_range_boundary_of_the_packed_kernels():
     seqs = ["AC" * 300, "AC" * 290 + "D" * 40, "C" * 610]
     check_stats(seqs, "BLOSUM62", 10, 25)
     check_stats(seqs, "BLOSUM62", 10, 26)
+
+
+def test_nw_plan_class_runs_twice_and_slices():
+    rng = np.random.default_rng(17)
+    seqs = random_seqs(rng, 70, 0, 420, "ARNDCQEGHILKMFPSTWYV")
+    want_m, want_l = port.nw_pair_stats(seqs, "BLOSUM80", 7, 2)
+    plan = da.NWPlan(seqs, "BLOSUM80", 7, 2)
+    assert plan.pairs == len(want_m) and plan.cells == sum(len(a) * len(b) for i, a in enumerate(seqs) for b in seqs[i:])
+    for _ in range(2):  # the plan is reusable
+        m, l = plan.run().fetch()
+        assert (m == want_m).all() and (l == want_l).all()
+    plan.close()
+    part = da.NWPlan(seqs, "BLOSUM80", 7, 2, row_begin=20, row_end=33)
+    m, l = part.run().fetch()
+    wm, wl = port.nw_pair_stats(seqs, "BLOSUM80", 7, 2, row_begin=20, row_end=33)
+    assert (m == wm).all() and (l == wl).all()
+    with pytest.raises(da.DynaAlignError, match="Invalid substitution matrix name: PAM250"):
+        da.NWPlan(seqs, "PAM250")
