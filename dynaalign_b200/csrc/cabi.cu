@@ -143,6 +143,12 @@ struct dyna_mh_plan {
   DevBuf<uint8_t> cub_temp;
   MhRelabelWork work;
   bool have_sequences = false, have_sig = false, have_sigT = false;
+  // Buffers are allocated and released through the stream-ordered allocator on the legacy default stream, while the
+  // work runs on whatever stream the caller passes.  Every entry point records that stream here and nothing is
+  // released (plan destruction, re-upload) before it has drained, so a released block can never still be in use --
+  // also when the caller's stream is a non-blocking one that the legacy stream does not wait for.
+  cudaStream_t last_stream = nullptr;
+  ~dyna_mh_plan() { cudaStreamSynchronize(last_stream); }
 };
 
 namespace {
@@ -234,10 +240,14 @@ extern "C" int dyna_mh_plan_upload_sequences(dyna_mh_plan* p, const uint8_t* res
   DYNA_TRY(use_device(p->device));
   if (k <= 0) return fail(DYNA_ERR_INVALID, "'k' must be a positive integer");
   if (k > 4096) return fail(DYNA_ERR_UNSUPPORTED, "k > 4096 is not supported");
+  DYNA_TRY(check_offsets(offsets, p->n, "dyna_mh_plan_upload_sequences"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t prev = p->last_stream;
+  p->last_stream = st;
   const int64_t total = offsets[p->n];
   p->max_len = 0;
   for (int64_t i = 0; i < p->n; ++i) p->max_len = std::max(p->max_len, offsets[i + 1] - offsets[i]);
+  if (p->have_sequences) DYNA_CUDA(cudaStreamSynchronize(prev));  // the old sequence buffers may still be in use
   DYNA_TRY(p->res.alloc((size_t)total + 8));
   DYNA_TRY(p->off.alloc((size_t)p->n + 1));
   DYNA_TRY(p->seeds.alloc((size_t)p->n_hash));
@@ -254,6 +264,7 @@ extern "C" int dyna_mh_plan_upload_signatures(dyna_mh_plan* p, const uint32_t* s
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   DYNA_CUDA(cudaMemcpyAsync(p->sig.p, sig, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyHostToDevice, st));
   int l = 0;
   DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l));
@@ -267,6 +278,7 @@ extern "C" int dyna_mh_plan_run_signatures(dyna_mh_plan* p, void* stream) {
   if (!p->have_sequences) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_signatures: no sequences uploaded");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
   int l = 0;
   DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l));
@@ -285,6 +297,7 @@ extern "C" int dyna_mh_plan_run_signatures_shard(dyna_mh_plan* p, int code_row_b
     return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_signatures_shard: bad code row range");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
   int l = 0;
   DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l, code_row_begin, code_row_end));
@@ -302,6 +315,7 @@ extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
   if (!p->have_sigT) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match: no signatures on the device");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   int l = 0;
   DYNA_TRY(launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, p->row_begin, p->row_end, p->counts.p,
                            p->use16 ? p->sigP.p : nullptr, p->use16 ? p->overflow.p : nullptr, st, &l));
@@ -313,6 +327,7 @@ extern "C" int dyna_mh_plan_fetch_signatures(dyna_mh_plan* p, uint32_t* sig_out,
   if (!p || !p->have_sig) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_fetch_signatures: nothing to fetch");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   DYNA_CUDA(cudaMemcpyAsync(sig_out, p->sig.p, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
   return DYNA_OK;
@@ -322,6 +337,7 @@ extern "C" int dyna_mh_plan_fetch_counts(dyna_mh_plan* p, uint16_t* counts_out, 
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   if (p->pairs > 0)
     DYNA_CUDA(cudaMemcpyAsync(counts_out, p->counts.p, sizeof(uint16_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
@@ -365,6 +381,7 @@ extern "C" int dyna_mh_plan_count_histogram(dyna_mh_plan* p, uint64_t* hist_out,
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   DevBuf<unsigned long long> d_hist;
   DYNA_TRY(d_hist.alloc((size_t)p->n_hash + 1));
   DYNA_TRY(launch_mh_count_hist(p->counts.p, p->pairs, p->n_hash, d_hist.p, st));
@@ -412,6 +429,7 @@ extern "C" int dyna_mh_plan_threshold_edges(dyna_mh_plan* p, int min_count, int6
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   const int64_t rows = p->row_end - p->row_begin;
   if (n_edges_out) *n_edges_out = 0;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
@@ -449,6 +467,7 @@ extern "C" int dyna_mh_plan_run_match_fetch(dyna_mh_plan* p, uint16_t* counts_ou
   if (!p->have_sigT) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match_fetch: no signatures on the device");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   const int64_t rows = p->row_end - p->row_begin;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
   const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, p->pairs / (64ll << 20)));
@@ -506,11 +525,14 @@ extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
 // =====================================================================================================
 struct NwClass {
   int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit,
-             // 6 two-pairs-per-warp 16-bit, several passes
+             // 6 two-pairs-per-warp 16-bit, several passes, 7 two-pairs-per-warp-pair 16-bit (cooperating warps)
   int R;
+  int64_t work = 0;  // DP cells of the class (launch order: largest first)
   std::vector<NwUnit> units;
   DevBuf<NwUnit> d_units;
 };
+
+constexpr int kNwSideStreams = 3;
 
 struct dyna_nw_plan {
   int device = 0;
@@ -526,6 +548,20 @@ struct dyna_nw_plan {
   DevBuf<uint32_t> matches, length;
   DevBuf<int32_t> scratch;
   DevBuf<uint4> scratch2;  // packed multi-pass kernel: boundary rows
+  // The kernel classes of one plan are independent (disjoint pairs): the largest runs on the caller's stream, the
+  // others on side streams forked from and joined back into it, so that small classes fill the tail of the large one
+  // instead of each paying its own tail (BASELINE config 2: one 45 ms launch and four launches of ~1 ms).
+  cudaStream_t side[kNwSideStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kNwSideStreams] = {nullptr, nullptr, nullptr};
+  cudaStream_t last_stream = nullptr;  // synchronised before any buffer is released (see DevBuf)
+  ~dyna_nw_plan() {
+    cudaStreamSynchronize(last_stream);
+    for (int i = 0; i < kNwSideStreams; ++i) {
+      if (side[i]) cudaStreamSynchronize(side[i]), cudaStreamDestroy(side[i]);
+      if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+  }
 };
 
 extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int64_t* offsets, int64_t n,
@@ -543,6 +579,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     fail(DYNA_ERR_INVALID, "dyna_nw_plan_create: bad row range");
     return nullptr;
   }
+  if (check_offsets(offsets, n, "dyna_nw_plan_create") != DYNA_OK) return nullptr;
   if (validate_residues(residues, offsets, n) != DYNA_OK) return nullptr;
   const int64_t total = n ? offsets[n] : 0;
   if (total >= (1ll << 31)) {
@@ -592,6 +629,14 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   int mp_min_rows = 32 * kNwWarp2MaxR + 1;  // 385..640 rows: single pass with tall strips measured faster (2.60 vs 2.25 TCUPS)
   if (const char* e = getenv("DYNA_NW_MP_MINROWS")) mp_min_rows = std::max(32 * 12 + 1, atoi(e));
   bool need_scratch2 = false;
+  // rows 385..768: two cooperating warps per pair-set (nw_warp2co_kernel); DYNA_NW_CO=0 restores the tall single-pass
+  // strips (385..640) and the multi-pass kernel (641..768) for A/B measurements
+  bool use_co = true;
+  if (const char* e = getenv("DYNA_NW_CO")) use_co = atoi(e) != 0;
+  // columns per unit of the packed single-pass kernel: wide units amortise the per-unit table build (+0.9 % at
+  // BASELINE config 5), but a small input needs the finer grain to fill 296 CTA slots (config 2: 2975 vs 2880 GCUPS)
+  int warp2_cols = p->pairs >= (int64_t)kNwWarp2UnitColsMax * kNwMultiPassGrid * 32 ? kNwWarp2UnitColsMax : kNwWarp2UnitCols;
+  if (const char* e = getenv("DYNA_NW_UNITCOLS")) warp2_cols = std::min(kNwWarp2UnitColsMax, std::max(2, atoi(e) & ~1));
 
   // encode residues, 32-bit offsets
   std::vector<uint8_t> codes((size_t)total + 4);
@@ -646,20 +691,26 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     return pack16 && hi <= 32000 && (int64_t)m + nmax <= 65535;
   };
   const bool force_warp2 = getenv("DYNA_NW_FORCE_WARP2") != nullptr;
+  std::vector<int64_t> len_prefix((size_t)n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) len_prefix[(size_t)i + 1] = len_prefix[(size_t)i] + (offsets[i + 1] - offsets[i]);
   for (int64_t i = row_begin; i < row_end; ++i) {
     const int m = (int)(offsets[i + 1] - offsets[i]);
     int64_t j = i;
     while (j < n) {
       int kind, R, step;
+      const bool co_rows = use_co && !force_warp2 && m >= kNwCoMinRows && m <= kNwCoMaxRows;
       if (m == 0) { kind = 0; R = 0; step = 4096; }
       else {
         // try the packed kernels on the widest unit they use; fall back to the 32-bit kernels for this stretch
-        const int pstep = nw_use_thread_kernel(m) && !force_warp2 ? 2 * kNwThreadUnitPairs : 2 * kNwWarpUnitPairs;
+        const bool warp2_rows = m <= 32 * kNwWarp2MaxR && (m < mp_min_rows || force_warp2);
+        const int pstep = nw_use_thread_kernel(m) && !force_warp2 ? 2 * kNwThreadUnitPairs
+                          : co_rows ? kNwCoUnitCols : warp2_rows ? warp2_cols : 2 * kNwWarpUnitPairs;
         const int64_t nmax = range_max(j, std::min<int64_t>(j + pstep, n));
         const bool p16 = fits16u(m, nmax);
         if (force_warp2 && p16 && nmax <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = std::max(2, nw_warp_R(m)); step = pstep; }
         else if (nw_use_thread_kernel(m) && p16) { kind = 5; R = nw_thread_R(m); step = pstep; }
         else if (nw_use_thread_kernel(m)) { kind = 1; R = nw_thread_R(m); step = kNwThreadUnitPairs; }
+        else if (co_rows && p16 && nmax <= kNwWarp2MaxCols) { kind = 7; R = nw_co_R(m); step = pstep; }
         else if (p16 && nmax <= kNwWarp2MaxCols && m < mp_min_rows && m <= 32 * kNwWarp2MaxR) { kind = 4; R = nw_warp_R(m); step = pstep; }
         else if (p16 && nmax <= kNwWarp2MpMaxCols && m > 32 * 6 && m <= kNwWarp2MpMaxRows) {
           // long rows, or columns too long for the single-pass kernel's staging buffer: the multi-pass form
@@ -669,12 +720,18 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
         else if (m <= 32 * kNwWarpMaxR) { kind = 2; R = nw_warp_R(m); step = kNwWarpUnitPairs; }
         else { kind = 3; R = kNwWarpMaxR; step = 8; need_scratch = true; }
       }
+      // the multi-pass kernel keeps one scratch line per pair-set: at most 64 columns per unit
+      if (kind == 6) step = std::min(step, 2 * kNwWarpUnitPairs);
       const int64_t cnt = std::min<int64_t>(step, n - j);
-      get_class(kind, R)->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
+      NwClass* cls = get_class(kind, R);
+      cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
+      cls->work += (int64_t)std::max(m, 1) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
       j += cnt;
     }
   }
 
+  std::stable_sort(p->classes.begin(), p->classes.end(),
+                   [](const std::unique_ptr<NwClass>& a, const std::unique_ptr<NwClass>& b) { return a->work > b->work; });
   timer.lap("nw plan: work units");
   if (p->codes.alloc(codes.size()) || p->off.alloc(off32.size()) || p->sub.alloc(576) ||
       p->matches.alloc((size_t)p->pairs) || p->length.alloc((size_t)p->pairs))
@@ -694,6 +751,16 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   if (!ok) {
     fail(DYNA_ERR_CUDA, "DynaAlign CUDA: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return nullptr;
+  }
+  if (p->classes.size() > 1 && !getenv("DYNA_NW_SERIAL")) {
+    bool sok = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kNwSideStreams && sok; ++i)
+      sok = cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!sok) {
+      fail(DYNA_ERR_CUDA, "DynaAlign CUDA: stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
   }
   timer.lap("nw plan: uploads");
   return p.release();
@@ -715,20 +782,51 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
   d.gap_ext = p->gap_ext;
   d.one = 1u;
   p->launches = 0;
+  p->last_stream = st;
+  const bool fork = p->side[0] != nullptr;
+  bool used[kNwSideStreams] = {false, false, false};
+  if (fork) DYNA_CUDA(cudaEventRecord(p->ev_fork, st));
+  int next_side = 0;
+  bool first = true;
+  cudaStream_t kind_stream[8] = {};
+  bool kind_stream_set[8] = {};
   for (auto& c : p->classes) {
     const int nu = (int)c->units.size();
     if (nu == 0) continue;
+    cudaStream_t cs = st;
+    // the two multi-pass kernels keep per-plan scratch lines: all classes of one such kind share ONE stream (which is
+    // the caller's stream if the largest class happens to be of that kind)
+    const bool scratch_kind = (c->kind == 3 || c->kind == 6);
+    if (scratch_kind && kind_stream_set[c->kind]) {
+      cs = kind_stream[c->kind];
+    } else if (fork && !first) {
+      const int si = next_side++ % kNwSideStreams;
+      if (!used[si]) DYNA_CUDA(cudaStreamWaitEvent(p->side[si], p->ev_fork, 0));
+      used[si] = true;
+      cs = p->side[si];
+    }
+    if (scratch_kind) {
+      kind_stream_set[c->kind] = true;
+      kind_stream[c->kind] = cs;
+    }
+    first = false;
     switch (c->kind) {
-      case 0: DYNA_TRY(launch_nw_empty_rows(d, c->d_units.p, nu, st)); break;
-      case 1: DYNA_TRY(launch_nw_thread(c->R, p->slant, d, c->d_units.p, nu, st)); break;
-      case 2: DYNA_TRY(launch_nw_warp(c->R, p->slant, false, d, c->d_units.p, nu, nullptr, 0, st)); break;
-      case 4: DYNA_TRY(launch_nw_warp2(c->R, d, c->d_units.p, nu, st)); break;
-      case 5: DYNA_TRY(launch_nw_thread2(c->R, d, c->d_units.p, nu, st)); break;
-      case 6: DYNA_TRY(launch_nw_warp2mp(c->R, d, c->d_units.p, nu, p->scratch2.p, st)); break;
-      default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, st)); break;
+      case 0: DYNA_TRY(launch_nw_empty_rows(d, c->d_units.p, nu, cs)); break;
+      case 1: DYNA_TRY(launch_nw_thread(c->R, p->slant, d, c->d_units.p, nu, cs)); break;
+      case 2: DYNA_TRY(launch_nw_warp(c->R, p->slant, false, d, c->d_units.p, nu, nullptr, 0, cs)); break;
+      case 4: DYNA_TRY(launch_nw_warp2(c->R, d, c->d_units.p, nu, cs)); break;
+      case 5: DYNA_TRY(launch_nw_thread2(c->R, d, c->d_units.p, nu, cs)); break;
+      case 6: DYNA_TRY(launch_nw_warp2mp(c->R, d, c->d_units.p, nu, p->scratch2.p, cs)); break;
+      case 7: DYNA_TRY(launch_nw_warp2co(c->R, d, c->d_units.p, nu, cs)); break;
+      default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, cs)); break;
     }
     ++p->launches;
   }
+  for (int i = 0; i < kNwSideStreams; ++i)
+    if (used[i]) {
+      DYNA_CUDA(cudaEventRecord(p->ev_join[i], p->side[i]));
+      DYNA_CUDA(cudaStreamWaitEvent(st, p->ev_join[i], 0));
+    }
   return DYNA_OK;
 }
 
@@ -736,6 +834,7 @@ extern "C" int dyna_nw_plan_fetch(dyna_nw_plan* p, uint32_t* matches_out, uint32
   if (!p) return fail(DYNA_ERR_INVALID, "null plan");
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
   if (p->pairs > 0) {
     DYNA_CUDA(cudaMemcpyAsync(matches_out, p->matches.p, sizeof(uint32_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
     DYNA_CUDA(cudaMemcpyAsync(length_out, p->length.p, sizeof(uint32_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
@@ -841,6 +940,7 @@ extern "C" int dyna_mh_signatures_linear(const int32_t* ranks, const int64_t* ra
   for (int h = 0; h < n_hash; ++h)
     if (a[h] < 0 || b[h] < 0 || a[h] >= (1ll << 31) || b[h] >= (1ll << 31))
       return fail(DYNA_ERR_UNSUPPORTED, "hash parameters must be in [0, 2^31)");
+  DYNA_TRY(check_offsets(rank_offsets, n, "dyna_mh_signatures_linear"));
   DYNA_TRY(use_device(g_device));
   const int64_t total = rank_offsets[n];
   for (int64_t q = 0; q < total; ++q)
@@ -972,6 +1072,9 @@ extern "C" int dyna_mh_match_matrix(const uint32_t* sig, int64_t n, int n_hash, 
   DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
   if (n < 2 * 128 * gpus) gpus = 1;
   if (gpus == 1) {
+    DYNA_TRY(use_device(g_device));
+    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)n + 2.0 * (double)tri_strict_rows(n, n), g_device,
+                               "dyna_mh_match_matrix: the n x n double matrix"));
     dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
     if (!p) return plan_error_code_mh();
     int rc = dyna_mh_plan_upload_signatures(p, sig, nullptr);
@@ -986,6 +1089,7 @@ extern "C" int dyna_mh_match_matrix(const uint32_t* sig, int64_t n, int n_hash, 
 extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets, int64_t n, int k, int n_hash,
                                  const uint32_t* seeds, double* out, int n_gpus) {
   DYNA_TRY(check_mh_args(n, k, n_hash));
+  DYNA_TRY(check_offsets(offsets, n, "dyna_similarityMH"));
   std::vector<uint32_t> own;
   if (!seeds) {  // reference behaviour: HashFamily(n_hash) seeded from std::random_device (src/minHash.cpp:73,137)
     own.resize((size_t)n_hash);
@@ -1002,6 +1106,9 @@ extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets
   };
   if (gpus == 1) {
     PhaseTimer tm;
+    DYNA_TRY(use_device(g_device));
+    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)n + 2.0 * (double)tri_strict_rows(n, n), g_device,
+                               "similarityMH: the n x n double matrix"));
     dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
     if (!p) return plan_error_code_mh();
     tm.lap("mh plan create");
@@ -1062,10 +1169,15 @@ extern "C" int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets
   int gpus = 1;
   if (!matrix_name || find_table(matrix_name) < 0)
     return fail(DYNA_ERR_INVALID, "Invalid substitution matrix name: %s", matrix_name ? matrix_name : "(null)");
+  DYNA_TRY(check_offsets(offsets, n, "dyna_similarityNW"));
   DYNA_TRY(validate_residues(residues, offsets, n));
   DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
   if (n < 64 * gpus) gpus = 1;
   if (gpus == 1) {
+    DYNA_TRY(use_device(g_device));
+    // n x n doubles plus the (matches, length) slab of the whole triangle
+    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)n + 8.0 * (double)tri_diag_rows(n, n), g_device,
+                               "similarityNW: the n x n double matrix"));
     dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, 0, n, g_device);
     if (!p) return plan_error_code();
     int rc = dyna_nw_plan_run(p, nullptr);

@@ -9,7 +9,7 @@
 #include <cstring>
 #include <string>
 
-#include "../../include/dynaalign_b200.h"
+#include "dynaalign_b200.h"
 
 namespace dyna {
 
@@ -50,7 +50,8 @@ inline int fail(int code, const char* fmt, ...) {
 // Device memory comes from the stream-ordered allocator with the pool's release threshold lifted, so the buffers of
 // one call are recycled by the next (clusterbreak invokes sim_fn once per recursion node; plain cudaMalloc/cudaFree of
 // the multi-GB result buffers was measured at up to 1 s per call).  All allocation and release is ordered on the
-// legacy default stream.
+// legacy default stream; the owners (plans, entry points) synchronise the stream their work ran on BEFORE releasing,
+// so a block handed to the next allocation is never still in use, whatever kind of stream the caller passed.
 inline void dev_pool_keep_cached(int device) {
   static bool done[64] = {false};
   if (device < 0 || device >= 64 || done[device]) return;
@@ -84,6 +85,43 @@ struct DevBuf {
     n = 0;
   }
 };
+
+// offsets[0..n] must start at 0 or above and never decrease (they come from a foreign caller: R, ctypes, ...)
+inline int check_offsets(const int64_t* offsets, int64_t n, const char* who) {
+  if (n < 0) return fail(DYNA_ERR_INVALID, "%s: negative sequence count", who);
+  if (n > 0 && !offsets) return fail(DYNA_ERR_INVALID, "%s: null offsets", who);
+  if (n > 0 && offsets[0] < 0) return fail(DYNA_ERR_INVALID, "%s: offsets[0] = %lld is negative", who, (long long)offsets[0]);
+  for (int64_t i = 0; i < n; ++i)
+    if (offsets[i + 1] < offsets[i])
+      return fail(DYNA_ERR_INVALID, "%s: offsets must be non-decreasing (offsets[%lld] = %lld > offsets[%lld] = %lld)", who,
+                  (long long)i, (long long)offsets[i], (long long)(i + 1), (long long)offsets[i + 1]);
+  return DYNA_OK;
+}
+
+// Will `bytes` more device memory fit?  Counts what the driver reports free plus what the (never trimmed) default pool
+// holds cached.  Lets the R-facing calls refuse an n x n double matrix that cannot exist with DYNA_ERR_UNSUPPORTED and
+// the byte count instead of a raw out-of-memory error from the middle of the run.
+inline int check_device_fits(double bytes, int device, const char* what) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    return DYNA_OK;  // cannot tell: let the allocation itself decide
+  }
+  double avail = (double)free_b;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      avail += (double)(reserved - used);
+  }
+  if (bytes > avail)
+    return fail(DYNA_ERR_UNSUPPORTED,
+                "%s needs %.0f bytes of device memory but only %.0f are available on device %d; use the row-range / "
+                "edge-list entry points for inputs of this size",
+                what, bytes, avail, device);
+  return DYNA_OK;
+}
 
 inline int64_t tri_strict_index(int64_t n, int64_t i, int64_t j) { return i * n - i * (i + 1) / 2 + (j - i - 1); }
 inline int64_t tri_strict_rows(int64_t n, int64_t r) { return r * n - r * (r + 1) / 2; }  // pairs in rows [0,r)

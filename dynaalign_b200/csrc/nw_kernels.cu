@@ -57,6 +57,9 @@ struct Strip {
   static constexpr int RP = R + (R & 1);      // 16-bit entries per lane strip, padded to even
   static constexpr int RW = RP / 2;           // 32-bit words actually read per step
   static constexpr int RWS = (RP / 2) | 1;    // word stride between strips: odd -> conflict-free across lanes
+  // stride for 64-bit profile loads: 8-byte aligned and == 2 (mod 4) words, so the 16 lanes of a half-warp wavefront
+  // hit 16 distinct bank pairs (2, 6, 10 words)
+  static constexpr int RWS64 = ((RW + 1) / 4) * 4 + 2;
 };
 
 // PTX prmt with full selector semantics (bit 3 of a selector nibble replicates the sign of the selected byte;
@@ -331,6 +334,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -390,6 +398,98 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
   outF = F;
 }
 
+// VAR 3: ONE table.  Per residue class and lane a record of RW score-profile words followed by R increment words,
+// padded to a stride of 4*odd words, read only with 128-bit loads (conflict-free: the 8 lanes of a quarter-warp
+// wavefront hit 8 distinct 16-byte bank groups whatever class each lane reads, because the class stride is a multiple
+// of 128 bytes).  Against VAR 2 a column costs one address computation per sequence instead of two and
+// ceil((RW+R)/4) loads instead of RW + ceil(R/4); ncu on the first cooperative kernel showed the 32-bit tail loads of
+// VAR 2 (9th increment row, 5th profile word) paying 4 and 2 wavefronts each at strides 12 and 6.
+template <int R>
+struct Rec {
+  static constexpr int RW = Strip<R>::RW;
+  static constexpr int kWords = RW + R;
+  static constexpr int NQ = (kWords + 3) / 4;  // 128-bit loads per record
+  static constexpr int kStride = (NQ | 1) * 4; // words per lane record: a multiple of 4, an odd multiple
+  // first strip row that uses a word of quad q (profile word w serves rows 2w and 2w+1; increment word RW+k row k)
+  __host__ __device__ static constexpr int first_needed(int q) {
+    int best = R;
+    for (int i = 4 * q; i < 4 * q + 4 && i < kWords; ++i) {
+      const int row = i < RW ? 2 * i : i - RW;
+      if (row < best) best = row;
+    }
+    return best;
+  }
+  __host__ __device__ static constexpr int load_row(int q) { return first_needed(q) >= 2 ? first_needed(q) - 2 : 0; }  // two rows ahead
+};
+
+template <int R, int LANES>
+__device__ __forceinline__ void build_records(uint32_t* rec, const uint8_t* __restrict__ a, int m, int row0,
+                                              const int8_t* __restrict__ sub, int bias, int tid, int nthreads) {
+  using RC = Rec<R>;
+  for (int idx = tid; idx < 25 * LANES * RC::kStride; idx += nthreads) {
+    const int cls = idx / (LANES * RC::kStride);
+    const int rem = idx - cls * (LANES * RC::kStride);
+    const int ln = rem / RC::kStride, w = rem - ln * RC::kStride;
+    uint32_t v = 0u;
+    if (w < RC::RW) {  // two 16-bit profile entries: low byte = int8 score (+ bias), high byte = residues equal
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * w + h, r = row0 + ln * R + k;
+        if (k < R && r < m && cls < 24) {
+          const int ar = a[r];
+          v |= ((uint32_t)(uint8_t)(sub[ar * 24 + cls] + bias) | (ar == cls ? 0x100u : 0u)) << (16 * h);
+        }
+      }
+    } else if (w < RC::kWords) {  // 1 | (row residue == class) << 16; padding rows and class 24 count steps only
+      const int k = w - RC::RW, r = row0 + ln * R + k;
+      v = 1u | ((r < m && cls < 24 && a[r] == cls) ? 0x10000u : 0u);
+    }
+    rec[idx] = v;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void strip_column3(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
+                                              const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
+                                              uint32_t (&SBn)[R], uint32_t recA, uint32_t recB, uint32_t diagH,
+                                              uint32_t dSA, uint32_t dSB, uint32_t F, uint32_t upSA, uint32_t upSB,
+                                              uint32_t ngo2, const Stat2Consts& c, uint32_t& outF) {
+  using RC = Rec<R>;
+  uint32_t wa[RC::NQ * 4], wb[RC::NQ * 4];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+#pragma unroll
+    for (int q = 0; q < RC::NQ; ++q) {
+      if (RC::load_row(q) == k) {
+        const uint4 va = lds_v4(recA + 16u * (unsigned)q), vb = lds_v4(recB + 16u * (unsigned)q);
+        wa[4 * q + 0] = va.x; wa[4 * q + 1] = va.y; wa[4 * q + 2] = va.z; wa[4 * q + 3] = va.w;
+        wb[4 * q + 0] = vb.x; wb[4 * q + 1] = vb.y; wb[4 * q + 2] = vb.z; wb[4 * q + 3] = vb.w;
+      }
+    }
+    const uint32_t wA = wa[k >> 1], wB = wb[k >> 1];
+    const uint32_t sP = (k & 1) ? prmt<0xE6A2>(wA, wB) : prmt<0xC480>(wA, wB);  // [sext16(sA) | sext16(sB) << 16]
+    const uint32_t incA = wa[RC::RW + k], incB = wb[RC::RW + k];
+    const uint32_t E = El[k];
+    const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    bool puB, puA, pdB, pdA;
+    const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);
+    const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    const uint32_t SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
+    diagH = Ho[k];
+    dSA = SAo[k];
+    dSB = SBo[k];
+    Hn[k] = H;
+    SAn[k] = SA;
+    SBn[k] = SB;
+    El[k] = __viaddmax_s16x2(H, ngo2, E);
+    F = __viaddmax_s16x2(H, ngo2, F);
+    upSA = SA;
+    upSB = SB;
+  }
+  outF = F;
+}
+
 // INPLACE: one register set for (H, S) instead of the ping-pong pair -- 4R instead of 7R state registers at the price
 // of three register moves per row (they issue as IMAD.MOV, off the ALU pipe).  Used for tall strips (R >= 13), where
 // the ping-pong version drops to one CTA per SM.
@@ -408,7 +508,9 @@ struct Warp2Smem {
   static constexpr int kIncStride = R <= 4 ? 4 : (R <= 12 ? 12 : 20);
   // score-profile stride per lane strip (odd word count: conflict-free 32-bit loads).  A 128-bit-load layout of the
   // score profile was measured slower (2.76 vs 2.94 TCUPS) and is not kept.
-  static constexpr int kProfStride = Strip<R>::RWS;
+  // VAR 2 reads it with 64-bit loads (stride == 2 mod 4 words: conflict-free for the 16 lanes of a wavefront).
+  static constexpr bool kProf64 = false;  // measured on the SASS: the register pairs of 64-bit loads cost more moves than the loads save (R = 11: 422 vs 394 instructions per two steps)
+  static constexpr int kProfStride = kProf64 ? Strip<R>::RWS64 : Strip<R>::RWS;
   static constexpr int kProfBytes = 25 * 32 * kProfStride * 4;
   static constexpr int kIncBytes = VAR == 2 ? 25 * 32 * kIncStride * 4 : 0;
   static constexpr int kStageBytes = (THREADS / 32) * 2 * (STAGE + 8);
@@ -443,11 +545,11 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   }
   // results of one unit (<= 64 consecutive pair slots), written back as two coalesced 256-byte rows instead of one
   // 4-byte store per pair (ncu: the scattered stores cost 30 % extra DRAM write traffic plus read-modify-write reads)
-  __shared__ uint32_t res_m[2 * kNwWarpUnitPairs], res_l[2 * kNwWarpUnitPairs];
+  __shared__ uint32_t res_m[kNwWarp2UnitColsMax], res_l[kNwWarp2UnitColsMax];
   // the unit's column sequences ordered by decreasing length: the two sequences that share a warp then differ by a
   // residue or two instead of the ~11 of a random pairing (the shorter one idles for the difference)
-  __shared__ int col_len[2 * kNwWarpUnitPairs];
-  __shared__ uint8_t col_ord[2 * kNwWarpUnitPairs];
+  __shared__ int col_len[kNwWarp2UnitColsMax];
+  __shared__ uint8_t col_ord[kNwWarp2UnitColsMax];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int go = d.gap_open, ge = d.gap_ext;
   const uint32_t ngo2 = pack16(-go);
@@ -467,7 +569,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int row = un.row;
     const int m = d.off[row + 1] - d.off[row];
     __syncthreads();
-    if (tid < un.j_count) col_len[tid] = d.off[un.j_begin + tid + 1] - d.off[un.j_begin + tid];
+    for (int q = tid; q < un.j_count; q += THREADS) col_len[q] = d.off[un.j_begin + q + 1] - d.off[un.j_begin + q];
     build_profile<R, 32, L::kProfStride>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
     for (int idx = tid; idx < 32 * L::kProfStride; idx += THREADS) prof[24 * 32 * L::kProfStride + idx] = 0u;
     if (VAR == 2) {  // increment table: 1 | (row residue == class) << 16; padding rows and class 24 count steps only
@@ -481,14 +583,14 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       }
     }
     __syncthreads();
-    if (tid < un.j_count) {  // rank by (length descending, index ascending): a permutation of 0..j_count-1
-      const int mine = col_len[tid];
+    for (int me = tid; me < un.j_count; me += THREADS) {  // rank by (length descending, index ascending): a permutation
+      const int mine = col_len[me];
       int rank = 0;
       for (int q = 0; q < un.j_count; ++q) {
         const int other = col_len[q];
-        rank += (other > mine || (other == mine && q < tid)) ? 1 : 0;
+        rank += (other > mine || (other == mine && q < me)) ? 1 : 0;
       }
-      col_ord[rank] = (uint8_t)tid;
+      col_ord[rank] = (uint8_t)me;
     }
     __syncthreads();
     const int lm = (m - 1) / R;
@@ -571,10 +673,23 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
             const uint32_t pb = plane_sh + cB * (32u * L::kProfStride * 4u);
             const uint32_t ia = ilane_sh + cA * (32u * L::kIncStride * 4u);
             const uint32_t ib = ilane_sh + cB * (32u * L::kIncStride * 4u);
+            if constexpr (L::kProf64) {
 #pragma unroll
-            for (int w = 0; w < S::RW; ++w) {
-              pwA[w] = lds_u32(pa + 4u * (unsigned)w);
-              pwB[w] = lds_u32(pb + 4u * (unsigned)w);
+              for (int w = 0; w < S::RW; w += 2) {  // an odd RW reads one padding word of the lane's stride
+                const uint2 va = lds_v2(pa + 4u * (unsigned)w), vb = lds_v2(pb + 4u * (unsigned)w);
+                pwA[w] = va.x;
+                pwB[w] = vb.x;
+                if (w + 1 < S::RW) {
+                  pwA[w + 1] = va.y;
+                  pwB[w + 1] = vb.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int w = 0; w < S::RW; ++w) {
+                pwA[w] = lds_u32(pa + 4u * (unsigned)w);
+                pwB[w] = lds_u32(pb + 4u * (unsigned)w);
+              }
             }
             if constexpr (INPLACE) {
               strip_column2<R, VAR>(H0, H0, El, SA0, SA0, SB0, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
@@ -815,6 +930,310 @@ nw_warp2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
           }
         }
         __syncwarp();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5x2 cooperative: K warps share one 32*K-lane wavefront (rows 385..768: the 566-residue HA sequences of BASELINE
+// config 2).  A strip taller than 12 rows per lane loses the ping-pong register sets and the increment table
+// (nw_warp2_kernel<R >= 13>: one register set, PRMT increments, 2.6 TCUPS against 3.2 for R <= 12); here the row
+// sequence is cut into K consecutive blocks of 32*R rows, R <= 12, and warp w of a group owns block w with exactly
+// the strip code of the fast kernel.  Warp w+1's lane 0 needs, per column, the bottom row (H, F', statA, statB) of
+// warp w's lane 31.  It travels through a 128-entry shared-memory ring:
+//   * lane 0 of the PRODUCER receives lane 31's bottom row one step later through the rotating shuffle every lane
+//     uses anyway (src = lane-1 mod 32), so the four values already sit in four fresh registers: one predicated
+//     128-bit store, no register moves, no divergent lane-31 code;
+//   * lane 0 of the CONSUMER overwrites the four shuffled registers with one predicated 128-bit load; the first
+//     warp of a group loads the constant border entry the same way (no per-step selects for the border row);
+//   * the two warps are NOT in lock step: each runs its own stream of (n + 31)-step jobs, the consumer trailing by
+//     at least 32 columns.  Progress counters (entries produced / consumed, published every 16 steps with
+//     st.release / ld.acquire at CTA scope) keep the consumer behind the producer and the producer less than one
+//     ring ahead; they are polled only when the cached copy says "not yet".
+// Warp-steps per pair-set are K*(n+31), the same as K sequential passes, and nothing leaves the SM (the multi-pass
+// kernel pays a global scratch line and a table rebuild per pass).  One CTA of 16 warps per SM: both warps' tables
+// (K*38 KB increments, K*16..22 KB scores) are resident, 8 groups share them.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoThreads = 512;
+constexpr int kCoRing = 128;   // ring entries (16 bytes each) between two neighbouring warps of a group
+constexpr int kCoChunk = 16;   // flow control and progress publication once per kCoChunk steps
+constexpr int kCoGap = 32;     // ring indices skipped between pair-sets (see the unconditional store below)
+
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int R, int K, int VAR>
+struct CoSmem {
+  static constexpr int kLanes = 32 * K;
+  static constexpr int kWarps = kCoThreads / 32;
+  static constexpr int kGroups = kWarps / K;
+  static constexpr int kIncStride = R <= 4 ? 4 : 12;  // multiple of 4 words, odd multiple: conflict-free 128-bit loads
+  static constexpr int kProfStride = Strip<R>::RWS64; // score profile read with 64-bit loads
+  static constexpr int kRingBytes = kWarps * kCoRing * 16;  // one outgoing ring per warp (the last warp's is a sink)
+  static constexpr int kRecStride = Rec<R>::kStride;  // VAR 3: one record table instead of the two tables
+  static constexpr int kIncBytes = VAR == 3 ? 25 * kLanes * kRecStride * 4 : 25 * kLanes * kIncStride * 4;
+  static constexpr int kProfBytes = VAR == 3 ? 0 : 25 * kLanes * kProfStride * 4;
+  static constexpr int kStageBytes = kWarps * 2 * (kNwStageCols + 8);  // every warp stages its own copy
+  // offsets from the first 2048-byte aligned address of the dynamic window (ring addresses are formed with OR)
+  static constexpr int kRingOff = 0;
+  static constexpr int kIncOff = kRingOff + kRingBytes;
+  static constexpr int kProfOff = kIncOff + kIncBytes;
+  static constexpr int kStageOff = kProfOff + kProfBytes;
+  static constexpr int kTotal = kStageOff + kStageBytes + 2048;
+  static_assert(R <= 12, "increment table stride");
+  static_assert(kWarps % K == 0, "groups");
+  static_assert(kCoRing * 16 == 2048, "ring addresses: (offset & 0x7F0) | base");
+};
+
+template <int R, int K, int VAR>
+__global__ void __launch_bounds__(kCoThreads, 1)
+nw_warp2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  using S = Strip<R>;
+  using L = CoSmem<R, K, VAR>;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ uint32_t res_m[kNwCoUnitCols], res_l[kNwCoUnitCols];
+  __shared__ int col_len[kNwCoUnitCols];
+  __shared__ uint8_t col_ord[kNwCoUnitCols];
+  __shared__ uint32_t prod_cnt[L::kWarps], cons_cnt[L::kWarps];  // per warp: ring entries it has written / read
+  const uint32_t dyn_sh = ((uint32_t)__cvta_generic_to_shared(smem_dyn) + 2047u) & ~2047u;
+  unsigned char* dyn = smem_dyn + (dyn_sh - (uint32_t)__cvta_generic_to_shared(smem_dyn));
+  uint32_t* incT = reinterpret_cast<uint32_t*>(dyn + L::kIncOff);
+  uint32_t* prof = reinterpret_cast<uint32_t*>(dyn + L::kProfOff);
+  uint8_t* stage_base = dyn + L::kStageOff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int group = warp / K, role = warp - group * K;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.one - 1u;
+  const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // register operand (see nw_thread2_kernel)
+  const uint32_t bord2 = pack16(ge - go);
+  const unsigned full = 0xFFFFFFFFu;
+  const int src_lane = (lane + 31) & 31;
+  const bool producer = role < K - 1, consumer = role > 0;
+  uint8_t* sA = stage_base + (warp * 2 + 0) * (kNwStageCols + 8);
+  uint8_t* sB = stage_base + (warp * 2 + 1) * (kNwStageCols + 8);
+  const uint32_t sA_sh = (uint32_t)__cvta_generic_to_shared(sA), sB_sh = (uint32_t)__cvta_generic_to_shared(sB);
+  const uint32_t plane_sh = (uint32_t)__cvta_generic_to_shared(prof + (role * 32 + lane) * L::kProfStride);
+  const uint32_t ilane_sh = (uint32_t)__cvta_generic_to_shared(incT + (role * 32 + lane) * (VAR == 3 ? L::kRecStride : L::kIncStride));
+  // Every warp writes its bottom row into its own ring; warp w > 0 of a group reads warp w-1's ring.  The first warp of
+  // a group "reads" entry 0 of the sink ring of the group's last warp, which holds the border constants for the whole
+  // unit (offset mask 0); the last warp's own stores go to entries 1.. of that sink ring and are never read.
+  const uint32_t out_ring_sh = dyn_sh + L::kRingOff + (uint32_t)warp * (kCoRing * 16);
+  const uint32_t in_ring_sh = dyn_sh + L::kRingOff + (uint32_t)(consumer ? warp - 1 : group * K + K - 1) * (kCoRing * 16);
+  const uint32_t in_mask16 = consumer ? (uint32_t)(kCoRing * 16 - 16) : 0u;
+  const uint32_t out_mask16 = (uint32_t)(kCoRing * 16 - 16);
+  const uint32_t out_fix = producer ? 0u : 16u;  // keeps the sink's stores away from entry 0 (see above)
+  const uint32_t my_prod_sh = (uint32_t)__cvta_generic_to_shared(&prod_cnt[warp]);
+  const uint32_t my_cons_sh = (uint32_t)__cvta_generic_to_shared(&cons_cnt[warp]);
+  const uint32_t up_prod_sh = (uint32_t)__cvta_generic_to_shared(&prod_cnt[consumer ? warp - 1 : warp]);
+  const uint32_t dn_cons_sh = (uint32_t)__cvta_generic_to_shared(&cons_cnt[producer ? warp + 1 : warp]);
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row;
+    const int m = d.off[row + 1] - d.off[row];
+    const uint8_t* __restrict__ a = d.codes + d.off[row];
+    __syncthreads();
+    if (tid < un.j_count) col_len[tid] = d.off[un.j_begin + tid + 1] - d.off[un.j_begin + tid];
+    if (tid < L::kWarps) prod_cnt[tid] = cons_cnt[tid] = 0u;
+    if (tid < L::kGroups)  // border entry of each group: H_diag = -go+ge (slanted), F = sentinel, no statistics yet
+      *reinterpret_cast<uint4*>(dyn + L::kRingOff + (tid * K + K - 1) * (kCoRing * 16)) = make_uint4(bord2, sent2, 0u, 0u);
+    if constexpr (VAR == 3) {
+      build_records<R, L::kLanes>(incT, a, m, 0, d.sub, 2 * ge, tid, kCoThreads);
+    } else {
+      build_profile<R, L::kLanes, L::kProfStride>(prof, a, m, 0, d.sub, 2 * ge, tid, kCoThreads);
+      for (int idx = tid; idx < L::kLanes * L::kProfStride; idx += kCoThreads) prof[24 * L::kLanes * L::kProfStride + idx] = 0u;
+      for (int idx = tid; idx < 25 * L::kLanes * L::kIncStride; idx += kCoThreads) {
+        const int cls = idx / (L::kLanes * L::kIncStride);
+        const int rem = idx - cls * (L::kLanes * L::kIncStride);
+        const int ln = rem / L::kIncStride, k = rem - ln * L::kIncStride;
+        const int r = ln * R + k;
+        incT[idx] = 1u | ((k < R && r < m && cls < 24 && a[r] == cls) ? 0x10000u : 0u);
+      }
+    }
+    __syncthreads();
+    if (tid < un.j_count) {  // rank by (length descending, index ascending)
+      const int mine = col_len[tid];
+      int rank = 0;
+      for (int q = 0; q < un.j_count; ++q) {
+        const int other = col_len[q];
+        rank += (other > mine || (other == mine && q < tid)) ? 1 : 0;
+      }
+      col_ord[rank] = (uint8_t)tid;
+    }
+    __syncthreads();
+    const int Lm = (m - 1) / R;              // last lane (0 .. 32K-1) that owns rows
+    const int km = (m - 1) - Lm * R;
+    const int last_role = Lm >> 5;           // host guarantees last_role == K-1 (m > 32*R*(K-1))
+    const int lm = (role < last_role) ? 31 : (Lm & 31);
+    const bool owns_result = (role == last_role);
+    const int r0 = (role * 32 + lane) * R;
+    const int npairs2 = (un.j_count + 1) >> 1;
+    // Ring index space: a pair-set with nA columns owns indices [base, base + nA) followed by a gap of kCoGap unused
+    // indices.  The gap absorbs the stores lane 0 issues before lane 31 has produced anything (steps 0..31 of the
+    // NEXT pair-set write indices base-32 .. base-1), so the store needs no condition at all.
+    int base_p = 0, base_c = 0;       // first ring index of the current pair-set (written / read side)
+    int seen_prod = 0, seen_cons = 0; // cached copies of the neighbours' counters
+
+    for (int pp = group; pp < npairs2; pp += L::kGroups) {
+      const bool hasB = (2 * pp + 1 < un.j_count);
+      int jA = un.j_begin + col_ord[2 * pp];
+      int jB = hasB ? un.j_begin + col_ord[2 * pp + 1] : jA;
+      int nA = d.off[jA + 1] - d.off[jA], nB = d.off[jB + 1] - d.off[jB];
+      if (nB > nA) {
+        int tj = jA; jA = jB; jB = tj;
+        int tn = nA; nA = nB; nB = tn;
+      }
+      {
+        const uint8_t* __restrict__ bA = d.codes + d.off[jA];
+        const uint8_t* __restrict__ bB = d.codes + d.off[jB];
+        __syncwarp();
+        for (int q = lane; q < nA; q += 32) {
+          sA[q] = bA[q];
+          sB[q] = (q < nB) ? bB[q] : (uint8_t)24;
+        }
+        __syncwarp();
+      }
+      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        H0[k] = H1[k] = bord2;
+        El[k] = sent2;
+        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+      }
+      uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
+      uint32_t prevUpSA = 0u, prevUpSB = 0u;
+      uint32_t outF = sent2;
+      uint32_t resB = 0u;
+      const unsigned n_act = (lane <= lm) ? (unsigned)nA : 0u;
+      const int capB = (owns_result && lane == lm) ? nB - 1 : -1;
+      // a producer runs one extra (idle) step so that lane 0 also receives and stores lane 31's last column
+      const int T = nA + lm + (producer ? 1 : 0);
+      // running ring addresses: step t stores index base_p + t - 32 and loads index base_c + t
+      uint32_t out_addr = out_ring_sh | (((uint32_t)(base_p - 32) * 16u) & out_mask16) | out_fix;
+      uint32_t in_addr = in_ring_sh | (((uint32_t)base_c * 16u) & in_mask16);
+      for (int tc = 0; tc < T; tc += kCoChunk) {
+        const int tend = min(tc + kCoChunk, T);
+        // ---- flow control once per chunk, warp-uniform (all lanes hold the same counters)
+        if (consumer) {
+          const int need = base_c + min(tend, nA);  // ring indices below this are read in this chunk
+          while (seen_prod < need) seen_prod = (int)ld_acquire_shared(up_prod_sh);
+        }
+        if (producer) {
+          const int top = base_p + tend + 1 - 32;   // ring indices below this are written in this chunk
+          while (top - seen_cons > kCoRing) seen_cons = (int)ld_acquire_shared(dn_cons_sh);
+        }
+        if (lane == 0) {
+          if (producer) st_release_shared(my_prod_sh, (uint32_t)(base_p + max(tc - 32, 0)));
+          if (consumer) st_release_shared(my_cons_sh, (uint32_t)(base_c + min(tc, nA)));
+        }
+        for (int t0 = tc; t0 < tend; t0 += 2) {
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int jc = t0 + ph - lane;
+            uint32_t rH = __shfl_sync(full, ph == 1 ? H1[R - 1] : H0[R - 1], src_lane);
+            uint32_t rF = __shfl_sync(full, outF, src_lane);
+            uint32_t rSA = __shfl_sync(full, ph == 1 ? SA1[R - 1] : SA0[R - 1], src_lane);
+            uint32_t rSB = __shfl_sync(full, ph == 1 ? SB1[R - 1] : SB0[R - 1], src_lane);
+            // lane 0: what arrived from lane 31 is this warp's bottom row at column t - 32 -> ring; its own upper
+            // neighbour comes from the ring of the warp above (or the border entry)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.eq.u32 p, %6, 0;\n\t"
+                "@p st.shared.v4.u32 [%4], {%0, %1, %2, %3};\n\t"
+                "@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n\t}"
+                : "+r"(rH), "+r"(rF), "+r"(rSA), "+r"(rSB)
+                : "r"(out_addr), "r"(in_addr), "r"(lane)
+                : "memory");
+            out_addr = out_ring_sh | ((out_addr + 16u) & out_mask16) | out_fix;
+            in_addr = in_ring_sh | ((in_addr + 16u) & in_mask16);
+            if ((unsigned)jc < n_act) {
+              const uint32_t cA = lds_u8(sA_sh + (uint32_t)jc), cB = lds_u8(sB_sh + (uint32_t)jc);
+              if constexpr (VAR == 3) {
+                const uint32_t ra = ilane_sh + cA * (uint32_t)(L::kLanes * L::kRecStride * 4);
+                const uint32_t rb = ilane_sh + cB * (uint32_t)(L::kLanes * L::kRecStride * 4);
+                if (ph == 0) {
+                  strip_column3<R>(H0, H1, El, SA0, SA1, SB0, SB1, ra, rb, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+                } else {
+                  strip_column3<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, rb, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+                }
+              } else {
+                uint32_t pwA[S::RW], pwB[S::RW];
+                const uint32_t pa = plane_sh + cA * (uint32_t)(L::kLanes * L::kProfStride * 4);
+                const uint32_t pb = plane_sh + cB * (uint32_t)(L::kLanes * L::kProfStride * 4);
+                const uint32_t ia = ilane_sh + cA * (uint32_t)(L::kLanes * L::kIncStride * 4);
+                const uint32_t ib = ilane_sh + cB * (uint32_t)(L::kLanes * L::kIncStride * 4);
+#pragma unroll
+                for (int w = 0; w < S::RW; w += 2) {  // an odd RW reads one padding word of the lane's stride
+                  const uint2 va = lds_v2(pa + 4u * (unsigned)w), vb = lds_v2(pb + 4u * (unsigned)w);
+                  pwA[w] = va.x;
+                  pwB[w] = vb.x;
+                  if (w + 1 < S::RW) {
+                    pwA[w + 1] = va.y;
+                    pwB[w + 1] = vb.y;
+                  }
+                }
+                if (ph == 0) {
+                  strip_column2<R, 2>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                      ngo2, c, outF, ia, ib);
+                } else {
+                  strip_column2<R, 2>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                      ngo2, c, outF, ia, ib);
+                }
+              }
+              prevUpH = rH;
+              prevUpSA = rSA;
+              prevUpSB = rSB;
+              if (jc == capB) {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                  if (k == km) resB = (ph == 0) ? SB1[k] : SB0[k];
+              }
+            }
+          }
+        }
+      }
+      // the pair-set is complete on this warp: publish, so that a neighbour waiting on the tail can proceed
+      base_p += nA + kCoGap;
+      base_c += nA + kCoGap;
+      __syncwarp();
+      if (lane == 0) {
+        if (producer) st_release_shared(my_prod_sh, (uint32_t)base_p);
+        if (consumer) st_release_shared(my_cons_sh, (uint32_t)base_c);
+      }
+      if (owns_result) {
+        const bool in1 = (((lm + nA) & 1) != 0);
+        uint32_t resA = 0u;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if (k == km) resA = in1 ? SA1[k] : SA0[k];
+        resA = __shfl_sync(full, resA, lm);
+        resB = __shfl_sync(full, resB, lm);
+        if (lane == 0) {
+          res_m[jA - un.j_begin] = resA >> 16;
+          res_l[jA - un.j_begin] = (uint32_t)(m + nA) - (resA & 0xFFFFu);
+          if (hasB) {
+            res_m[jB - un.j_begin] = resB >> 16;
+            res_l[jB - un.j_begin] = (uint32_t)(m + nB) - (resB & 0xFFFFu);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int64_t slot0 = pair_slot(d.n, row, un.j_begin, d.slab_base);
+      for (int q = tid; q < 2 * un.j_count; q += kCoThreads) {
+        if (q < un.j_count) d.matches[slot0 + q] = res_m[q];
+        else d.length[slot0 + q - un.j_count] = res_l[q - un.j_count];
       }
     }
   }
@@ -1129,6 +1548,34 @@ int launch_nw_warp2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 #undef DYNA_CASE
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw warp2 multipass kernel: unsupported strip height %d", R);
+  }
+}
+
+template <int R, int VAR>
+int launch_warp2co_inst(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  using L = CoSmem<R, 2, VAR>;
+  DYNA_CUDA(cudaFuncSetAttribute(nw_warp2co_kernel<R, 2, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  nw_warp2co_kernel<R, 2, VAR><<<num_units, kCoThreads, L::kTotal, st>>>(d, d_units, num_units);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+template <int R>
+int launch_warp2co_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  const int var = getenv("DYNA_NW_CO_VARIANT") ? atoi(getenv("DYNA_NW_CO_VARIANT")) : 3;
+  if (var == 2) return launch_warp2co_inst<R, 2>(d, d_units, num_units, st);
+  return launch_warp2co_inst<R, 3>(d, d_units, num_units, st);
+}
+
+int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_warp2co_R<RR>(d, d_units, num_units, st);
+    DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9) DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw cooperative warp2 kernel: unsupported strip height %d", R);
   }
 }
 

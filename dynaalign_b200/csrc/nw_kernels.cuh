@@ -28,7 +28,11 @@ constexpr int kNwThreadMaxRows = 32;  // rows handled by the thread-per-pair ker
 constexpr int kNwWarpMaxR = 24;       // rows per lane of the warp-per-pair kernel (32*24 = 768 rows per pass)
 constexpr int kNwWarp2MaxCols = 1024;  // column-sequence length limit of the packed warp kernel (shared-memory staging)
 constexpr int kNwWarp2MaxR = 20;      // strip height limit of the two-pairs-per-warp 16-bit kernel (register budget)
-constexpr int kNwWarpUnitPairs = 32;  // pairs per unit (8 warps x 4)
+constexpr int kNwWarpUnitPairs = 32;  // pairs per unit (8 warps x 4) of the 32-bit warp kernel
+// column sequences per unit of the packed single-pass warp kernel: 64 by default, kNwWarp2UnitColsMax for large inputs
+// (chosen in cabi.cu); DYNA_NW_UNITCOLS overrides it for measurements
+constexpr int kNwWarp2UnitCols = 64;
+constexpr int kNwWarp2UnitColsMax = 256;
 constexpr int kNwThreadUnitPairs = 512;
 constexpr int kNwMultiPassGrid = 148 * 2;
 
@@ -48,6 +52,13 @@ int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num
 int launch_nw_thread2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 // packed kernel, several passes of 32*R rows (R in 7..12); scratch: kNwMultiPassGrid * 32 pair-sets * kNwWarp2MpMaxCols * 16 bytes
 int launch_nw_warp2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, void* d_scratch, cudaStream_t st);
+// cooperative packed kernel: two warps share one 64-lane wavefront (rows 385..768, R = ceil(m/64) in 7..12, so that the
+// second warp always owns rows); a unit is one row against up to kNwCoUnitCols column sequences
+constexpr int kNwCoUnitCols = 128;
+constexpr int kNwCoMinRows = 32 * 12 + 1;
+constexpr int kNwCoMaxRows = 64 * 12;
+inline int nw_co_R(int m) { return (m + 63) / 64; }
+int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 constexpr int kNwWarp2MpMaxRows = 32 * 12 * 8;  // 8 passes at most
 constexpr int kNwWarp2MpMaxCols = 2048;        // its column-sequence limit (staging buffer)
 // (matches, length) slab -> column-major doubles, both triangles (reference: src/pairwiseSeqAlign.cpp:311,349-350)

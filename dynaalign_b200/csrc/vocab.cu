@@ -53,6 +53,7 @@ extern "C" int dyna_minhash_vocab_ranks(const uint8_t* residues, const int64_t* 
                                         uint64_t* vocab_keys_out, int64_t vocab_capacity, int64_t* vocab_size_out,
                                         int32_t* ranks_out, int64_t* rank_offsets_out) {
   if (n <= 0) return fail(DYNA_ERR_INVALID, "Input sequences vector cannot be empty");
+  DYNA_TRY(check_offsets(offsets, n, "dyna_minhash_vocab_ranks"));
   // shingle()'s argument check, raised for the first offending sequence as lapply would (R/minHash.R:15-16)
   for (int64_t d = 0; d < n; ++d) {
     const int64_t L = offsets[d + 1] - offsets[d];

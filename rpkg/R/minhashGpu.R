@@ -57,8 +57,12 @@ compute_signature_matrix <- function(char_matrix, hash_params, max_val) {
 #' @export
 compute_distance_matrix <- function(sig_matrix) {
   # only equality matters: relabel every hash row to dense integer codes, then count matches on the GPU
-  codes <- t(apply(sig_matrix, 1, function(r) match(r, unique(r)) - 1L))
-  storage.mode(codes) <- "integer"
+  # (filled row by row: t(apply(...)) would come back transposed when there is a single document)
+  codes <- matrix(0L, nrow = nrow(sig_matrix), ncol = ncol(sig_matrix))
+  for (h in seq_len(nrow(sig_matrix))) {
+    r <- sig_matrix[h, ]
+    codes[h, ] <- match(r, unique(r)) - 1L
+  }
   .mh_distance_matrix(codes)
 }
 

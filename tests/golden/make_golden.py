@@ -3,7 +3,8 @@
 Run in the build container (where /root/reference exists and oracle/_ref has been built):
 
     python tests/golden/make_golden.py            # everything except the long C2 run
-    python tests/golden/make_golden.py --c2       # also h3n2sample[1:1000] NW stats (minutes, all cores)
+    python tests/golden/make_golden.py --c2       # also h3n2sample[1:1000] NW stats, every distinct pair checked
+                                                  # against the compiled reference (minutes, all cores)
 
 Inputs come from the reference's data/*.rda (read with dynaalign_b200.rda); outputs come from
 oracle/_ref/libdynaref.so (the reference's src/*.cpp compiled unmodified).  The fixtures are small
@@ -97,15 +98,47 @@ def main():
     print("golden.json written")
 
     if "--c2" in sys.argv:
-        # full config-2 NW (matches, length) with the validated port on all cores
+        # Full config-2 NW (matches, length).  The integers come from the C port (the reference only returns the
+        # double matches/length); BEFORE they are stored, every distinct ordered (row sequence, column sequence)
+        # combination that occurs among the 500,500 pairs is run through the compiled reference's own
+        # calculate_similarity (src/pairwiseSeqAlign.cpp:209-313) and the port's matches/length must reproduce that
+        # double exactly.  h3n2sample[1:1000] holds 449 distinct sequences, so this is ~1.0e5 reference alignments
+        # (a few CPU-minutes on all cores) instead of 5.0e5.
+        import multiprocessing as mp
         mt, ln = port.nw_pair_stats(h3)
-        # cross-check a sample against the reference before committing
-        n = 1000
-        for s in samp:
-            k = s["i"] * n - s["i"] * (s["i"] - 1) // 2 + (s["j"] - s["i"])
-            assert float(mt[k]) / float(ln[k]) == s["sim"], s
+        n = len(h3)
+        slot = {}
+        for i in range(n):
+            base = i * n - i * (i - 1) // 2 - i
+            ui = idx[i]
+            for j in range(i, n):
+                slot.setdefault((ui, idx[j]), base + j)
+        combos = sorted(slot)
+        with mp.Pool(os.cpu_count()) as pool:
+            sims = pool.starmap(_ref_sim, [(uniq[u], uniq[v]) for u, v in combos], chunksize=64)
+        bad = 0
+        for (u, v), sim in zip(combos, sims):
+            k = slot[(u, v)]
+            got = float(mt[k]) / float(ln[k]) if ln[k] else float("nan")
+            if not (got == sim or (np.isnan(got) and np.isnan(sim))):
+                bad += 1
+        assert bad == 0, "%d of %d distinct pairs differ from the compiled reference" % (bad, len(combos))
+        # every occurrence of a combination must carry the same integers (the port is deterministic per pair)
+        for i in range(0, n, 37):
+            base = i * n - i * (i - 1) // 2 - i
+            for j in range(i, n, 11):
+                k = slot[(idx[i], idx[j])]
+                assert mt[base + j] == mt[k] and ln[base + j] == ln[k]
         np.savez_compressed(os.path.join(HERE, "nw_h3n2_1000_stats.npz"), matches=mt.astype(np.uint16), length=ln.astype(np.uint16))
-        print("C2 stats written")
+        with open(os.path.join(HERE, "nw_h3n2_1000_stats.provenance.json"), "w") as f:
+            json.dump({"distinct_sequences": len(uniq), "distinct_ordered_pairs_checked_against_compiled_reference": len(combos),
+                       "mismatches": bad, "pairs_total": int(mt.size),
+                       "check": "float(matches)/float(length) == ref.calculate_similarity(row, column), bit-exact doubles"}, f, indent=1)
+        print("C2 stats written; all %d distinct ordered pairs checked against the compiled reference" % len(combos))
+
+
+def _ref_sim(a, b):
+    return ref.calculate_similarity(a, b)
 
 
 if __name__ == "__main__":

@@ -55,6 +55,33 @@ def test_warp_kernel_all_strip_heights(lo, hi):
     check_stats(seqs)
 
 
+@pytest.mark.parametrize("R", [7, 9, 10, 12])
+def test_cooperative_kernel_rows_385_to_768(R):
+    # rows of 385..768 residues: two warps share one 64-lane wavefront (nw_warp2co_kernel), units of 128 columns;
+    # lengths sit at the strip boundaries 64*(R-1)+1 .. 64*R, columns mix short, equal and > 1024 (fallback) lengths
+    rng = np.random.default_rng(100 + R)
+    lo, hi = max(385, 64 * (R - 1) + 1), 64 * R
+    fam = "".join(random_seqs(rng, 1, hi, hi, "ARNDCQEGHILKMFPSTWYV"))
+    seqs = [fam[: int(L)] for L in rng.integers(lo, hi + 1, size=70)]                    # related: long diagonal runs
+    seqs += random_seqs(rng, 50, lo, hi, "ARNDCQEGHILKMFPSTWYV")                         # unrelated: gaps and ties
+    seqs += [fam[:lo], fam[:hi], fam[5:hi], ""] + random_seqs(rng, 6, 1, 60) + random_seqs(rng, 2, 1025, 1040)
+    rng.shuffle(seqs)
+    check_stats(seqs)
+
+
+def test_cooperative_kernel_equals_single_warp_kernels():
+    # same input through the cooperative kernel and (DYNA_NW_CO=0) the tall-strip / multi-pass kernels
+    rng = np.random.default_rng(77)
+    seqs = random_seqs(rng, 150, 500, 700, "ARNDCQEGHILKMFPSTWYV")
+    a = da.nw_pair_stats(seqs, "BLOSUM80", 7, 2)
+    os.environ["DYNA_NW_CO"] = "0"
+    try:
+        b = da.nw_pair_stats(seqs, "BLOSUM80", 7, 2)
+    finally:
+        del os.environ["DYNA_NW_CO"]
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
 def test_warp_kernel_exact_boundaries():
     # row lengths at the strip boundaries 32*R and 32*R+1, against short and long columns
     rng = np.random.default_rng(9)

@@ -16,7 +16,7 @@ TABLES = ["BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90", "BLOSUM100
 
 
 def dataset(rng):
-    kind = rng.integers(0, 5)
+    kind = rng.integers(0, 7)
     if kind == 0:  # around one strip height R: lengths 31R-3 .. 32R+3 (rotation boundary and next height)
         R = int(rng.integers(2, 21))
         lens = rng.integers(max(1, 31 * R - 3), 32 * R + 4, size=int(rng.integers(60, 140)))
@@ -30,6 +30,15 @@ def dataset(rng):
     elif kind == 3:  # short probes with a few long columns
         lens = rng.integers(1, 33, size=int(rng.integers(80, 200)))
         lens[rng.integers(0, len(lens), 4)] = rng.integers(300, 1500, 4)
+    elif kind == 5:  # cooperative two-warp kernel: rows 385..768 around one strip height (64R-3 .. 64R+3), units of 128 columns
+        R = int(rng.integers(7, 13))
+        n = int(rng.choice([40, 127, 128, 129, 131]))
+        lens = rng.integers(max(385, 64 * (R - 1) - 3), min(768, 64 * R + 3) + 1, size=n)
+        lens[rng.integers(0, n, 6)] = [0, 1, 385, 768, 1024, 1030][: 6]
+    elif kind == 6:  # cooperative kernel: HA-like family (equal lengths, ties in the pairing) with a few outliers
+        base = int(rng.integers(500, 640))
+        lens = np.full(int(rng.choice([64, 130, 200])), base)
+        lens[rng.integers(0, len(lens), 8)] += rng.integers(-40, 40, 8)
     else:  # long rows (multi-pass) with mixed columns
         lens = np.concatenate([rng.integers(650, 1300, size=12), rng.integers(1, 600, size=20)])
     lens = np.maximum(lens, 0)
