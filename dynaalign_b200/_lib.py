@@ -35,6 +35,7 @@ _SIGS = {
     "dyna_version": (C.c_int, []),
     "dyna_device_count": (C.c_int, []),
     "dyna_set_device": (C.c_int, [C.c_int]),
+    "dyna_release_cached_memory": (C.c_int, [C.c_int]),
     "dyna_partition_rows": (C.c_int, [C.c_int64, _i64p, C.c_int, C.c_int, _i64p]),
     "dyna_hashfamily_seeds": (C.c_int, [C.c_uint32, C.c_int, _u32p]),
     "dyna_random_seed": (C.c_uint32, []),
@@ -47,6 +48,7 @@ _SIGS = {
     "dyna_substitution_matrix": (C.c_int, [C.c_char_p, _i8p]),
     "dyna_aa_index_table": (None, [_i8p]),
     "dyna_nw_pair_stats": (C.c_int, [_u8p, _i64p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _u32p]),
+    "dyna_nw_pair_stats8": (C.c_int, [_u8p, _i64p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, _u8p, _u8p]),
     "dyna_similarityNW": (C.c_int, [_u8p, _i64p, C.c_int64, C.c_char_p, C.c_int, C.c_int, _f64p, C.c_int]),
     "dyna_mh_plan_create": (C.c_void_p, [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int]),
     "dyna_mh_plan_upload_sequences": (C.c_int, [C.c_void_p, _u8p, _i64p, C.c_int, _u32p, C.c_void_p]),
@@ -65,6 +67,8 @@ _SIGS = {
     "dyna_mh_plan_count_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "dyna_quantile_type7_counts": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_double, _f64p, C.POINTER(C.c_int)]),
     "dyna_mh_plan_threshold_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _u16p, _i64p, C.c_void_p]),
+    "dyna_mh_plan_run_match_fetch8": (C.c_int, [C.c_void_p, _u8p, C.c_int64, _i64p, _u16p, _i64p, C.c_void_p]),
+    "dyna_mh_plan_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "dyna_mh_plan_pairs": (C.c_int64, [C.c_void_p]),
     "dyna_mh_plan_launches": (C.c_int, [C.c_void_p]),
     "dyna_mh_plan_counts_device_ptr": (C.c_void_p, [C.c_void_p]),
@@ -72,6 +76,8 @@ _SIGS = {
     "dyna_nw_plan_create": (C.c_void_p, [_u8p, _i64p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int]),
     "dyna_nw_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dyna_nw_plan_fetch": (C.c_int, [C.c_void_p, _u32p, _u32p, C.c_void_p]),
+    "dyna_nw_plan_fetch_packed8": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_void_p]),
+    "dyna_nw_plan_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "dyna_nw_plan_pairs": (C.c_int64, [C.c_void_p]),
     "dyna_nw_plan_cells": (C.c_int64, [C.c_void_p]),
     "dyna_nw_plan_launches": (C.c_int, [C.c_void_p]),

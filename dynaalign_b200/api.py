@@ -24,7 +24,8 @@ from ._lib import DynaAlignError, check, flatten, lib, ptr
 __all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
            "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
            "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
-           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "NWPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError"]
+           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "NWPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError",
+           "nw_pair_stats8", "checksum", "checksum_weights"]
 
 
 def dimnames(n):
@@ -113,6 +114,36 @@ def nw_pair_stats(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, row_be
     check(lib().dyna_nw_pair_stats(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, matrixName.encode(), int(gapOpen),
                                    int(gapExt), row_begin, row_end, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32)))
     return mt[:sz], ln[:sz]
+
+
+def nw_pair_stats8(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, row_begin=0, row_end=None):
+    """nw_pair_stats in the 2-bytes-per-pair host form (every sequence <= 127 residues): (matches u8, length u8)."""
+    sequences = list(sequences)
+    n = len(sequences)
+    row_end = n if row_end is None else row_end
+    res, off = flatten(sequences)
+    sz = tri_diag_size(n, row_begin, row_end)
+    mt = np.zeros(max(sz, 1), dtype=np.uint8)
+    ln = np.zeros(max(sz, 1), dtype=np.uint8)
+    check(lib().dyna_nw_pair_stats8(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, matrixName.encode(), int(gapOpen),
+                                    int(gapExt), row_begin, row_end, ptr(mt, C.c_uint8), ptr(ln, C.c_uint8)))
+    return mt[:sz], ln[:sz]
+
+
+def checksum_weights(first_index, count):
+    """w(k) of dyna_*_plan_checksum for global packed pair indices first_index .. first_index+count-1 (numpy uint64,
+    wrap-around arithmetic): x = (k+1) * 0x9E3779B97F4A7C15; w = x ^ (x >> 31)."""
+    with np.errstate(over="ignore"):
+        k = np.arange(first_index, first_index + count, dtype=np.uint64) + np.uint64(1)
+        x = k * np.uint64(0x9E3779B97F4A7C15)
+        return x ^ (x >> np.uint64(31))
+
+
+def checksum(values, first_index=0):
+    """Host restatement of the device checksum: sum(values[k] * w(first_index + k)) mod 2^64."""
+    v = np.asarray(values).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        return int((v * checksum_weights(first_index, v.size)).sum(dtype=np.uint64))
 
 
 def partition_rows(n, nshards, weights=None, include_diagonal=False):
@@ -232,6 +263,26 @@ class MinHashPlan:
             self._matched = True
         return out[:tri_strict_size(self.n)]
 
+    def match_counts8(self, esc_capacity=1 << 20):
+        """Match and fetch in the narrow form: (counts saturated at 255 as uint8, escape pair indices, escape counts);
+        the exact u16 triangle is counts8 with counts8[escape index] replaced by the escape count."""
+        sz = tri_strict_size(self.n)
+        out = np.zeros(max(sz, 1), dtype=np.uint8)
+        ei = np.zeros(max(esc_capacity, 1), dtype=np.int64)
+        ec = np.zeros(max(esc_capacity, 1), dtype=np.uint16)
+        ne = C.c_int64(0)
+        check(lib().dyna_mh_plan_run_match_fetch8(self._h, ptr(out, C.c_uint8), int(esc_capacity), ptr(ei, C.c_int64),
+                                                  ptr(ec, C.c_uint16), C.byref(ne), None))
+        self._matched = True
+        order = np.argsort(ei[:ne.value], kind="stable")
+        return out[:sz], ei[:ne.value][order], ec[:ne.value][order]
+
+    def checksum(self):
+        self._match()
+        h = C.c_uint64(0)
+        check(lib().dyna_mh_plan_checksum(self._h, C.byref(h), None))
+        return int(h.value)
+
     def histogram(self):
         self._match()
         hist = np.zeros(self.n_hash + 1, dtype=np.uint64)
@@ -290,6 +341,20 @@ class NWPlan:
         ln = np.zeros(max(sz, 1), dtype=np.uint32)
         check(lib().dyna_nw_plan_fetch(self._h, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32), None))
         return mt[:sz], ln[:sz]
+
+    def fetch_packed8(self):
+        """(matches, length) as uint8 each (2 bytes per pair); only when every alignment length fits a byte."""
+        sz = self.pairs
+        mt = np.zeros(max(sz, 1), dtype=np.uint8)
+        ln = np.zeros(max(sz, 1), dtype=np.uint8)
+        check(lib().dyna_nw_plan_fetch_packed8(self._h, ptr(mt, C.c_uint8), ptr(ln, C.c_uint8), None))
+        return mt[:sz], ln[:sz]
+
+    def checksum(self):
+        """(matches, length) position-weighted checksums of the plan's slab (see checksum())."""
+        h = (C.c_uint64 * 2)()
+        check(lib().dyna_nw_plan_checksum(self._h, h, None))
+        return int(h[0]), int(h[1])
 
     def close(self):
         if getattr(self, "_h", None):

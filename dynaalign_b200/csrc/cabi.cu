@@ -15,6 +15,7 @@
 
 #include "blosum_tables.h"
 #include "common.cuh"
+#include "gather.cuh"
 #include "mh_kernels.cuh"
 #include "nw_kernels.cuh"
 
@@ -54,6 +55,79 @@ int resolve_gpus(int n_gpus, int* out) {
     return fail(DYNA_ERR_CUDA, "DynaAlign CUDA: no usable CUDA device (%s); there is no CPU fallback",
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   *out = (n_gpus <= 0 || n_gpus > count) ? count : n_gpus;
+  return DYNA_OK;
+}
+
+// One process driving several GPUs: every device must be able to read the result slabs of the others (the expansion
+// kernels gather them with peer loads over NVLink).  Plain cudaDeviceEnablePeerAccess covers cudaMalloc memory; the
+// stream-ordered pools the buffers come from need cudaMemPoolSetAccess as well.  Returns false if any pair of the
+// first `gpus` devices cannot reach each other.
+bool enable_peer_mesh(int gpus) {
+  static std::mutex mu;
+  static int done_for = 0;
+  static bool ok_cached = true;
+  std::lock_guard<std::mutex> lock(mu);
+  if (gpus <= done_for) return ok_cached;
+  bool ok = true;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int a = 0; a < gpus && ok; ++a) {
+    if (cudaSetDevice(a) != cudaSuccess) { ok = false; break; }
+    dev_pool_keep_cached(a);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, a) != cudaSuccess) { ok = false; break; }
+    std::vector<cudaMemAccessDesc> descs;
+    for (int b = 0; b < gpus; ++b) {
+      if (b == a) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) { ok = false; break; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = false; break; }
+      cudaGetLastError();
+      cudaMemAccessDesc d{};
+      d.location.type = cudaMemLocationTypeDevice;
+      d.location.id = b;  // device b may read and write allocations of device a's pool
+      d.flags = cudaMemAccessFlagsProtReadWrite;
+      descs.push_back(d);
+    }
+    if (ok && !descs.empty() && cudaMemPoolSetAccess(pool, descs.data(), descs.size()) != cudaSuccess) ok = false;
+  }
+  cudaGetLastError();
+  cudaSetDevice(prev);
+  done_for = gpus;
+  ok_cached = ok;
+  return ok;
+}
+
+// columns [bounds[g], bounds[g+1]) of the n x n result are expanded and copied to the host by device g
+void column_blocks(int64_t n, int gpus, std::vector<int64_t>& bounds) {
+  bounds.resize((size_t)gpus + 1);
+  for (int g = 0; g <= gpus; ++g) bounds[(size_t)g] = n * g / gpus;
+}
+
+// Runs fn(g) on one host thread per device (inline when there is one), collects the first error.
+template <class Fn>
+int for_each_gpu(int gpus, Fn fn) {
+  std::vector<int> rcs((size_t)gpus, DYNA_OK);
+  std::vector<std::string> errs((size_t)gpus);
+  if (gpus == 1) {
+    rcs[0] = fn(0);
+    if (rcs[0] != DYNA_OK) errs[0] = err_slot();
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; ++g)
+      th.emplace_back([&, g]() {
+        rcs[(size_t)g] = fn(g);
+        if (rcs[(size_t)g] != DYNA_OK) errs[(size_t)g] = err_slot();  // err_slot() is thread-local
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int g = 0; g < gpus; ++g)
+    if (rcs[(size_t)g] != DYNA_OK) {
+      err_slot() = errs[(size_t)g];
+      err_code_slot() = rcs[(size_t)g];
+      return rcs[(size_t)g];
+    }
   return DYNA_OK;
 }
 
@@ -511,6 +585,104 @@ extern "C" int dyna_mh_plan_run_match_fetch(dyna_mh_plan* p, uint16_t* counts_ou
   return rc;
 }
 
+// Position-weighted checksum of the plan's counts slab (see gather.cu): additive over the slabs of a partition.
+extern "C" int dyna_mh_plan_checksum(dyna_mh_plan* p, uint64_t* sum_out, void* stream) {
+  if (!p || !sum_out) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_checksum: null argument");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  DevBuf<unsigned long long> d_sum;
+  DYNA_TRY(d_sum.alloc(1));
+  DYNA_TRY(launch_checksum_u16(p->counts.p, p->pairs, tri_strict_rows(p->n, p->row_begin), d_sum.p, st));
+  unsigned long long h = 0;
+  DYNA_CUDA(cudaMemcpyAsync(&h, d_sum.p, sizeof h, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  *sum_out = h;
+  return DYNA_OK;
+}
+
+// run_match_fetch in the narrow host form: one byte per pair (counts saturated at 255) plus the exact (pair index,
+// count) of every pair that reached 255 -- lossless, and half the device-to-host traffic of the u16 triangle, which is
+// what bounds the dense end-to-end rate (10 GB at BASELINE config 4).  Escapes arrive in no particular order.  If more
+// than esc_capacity pairs escape, *n_esc_out reports how many there are and the call fails with DYNA_ERR_INVALID.
+extern "C" int dyna_mh_plan_run_match_fetch8(dyna_mh_plan* p, uint8_t* counts8_out, int64_t esc_capacity, int64_t* esc_index_out,
+                                             uint16_t* esc_count_out, int64_t* n_esc_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (!p->have_sigT) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match_fetch8: no signatures on the device");
+  if (esc_capacity < 0 || (esc_capacity > 0 && (!esc_index_out || !esc_count_out)))
+    return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match_fetch8: bad escape buffers");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  if (n_esc_out) *n_esc_out = 0;
+  const int64_t rows = p->row_end - p->row_begin;
+  if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
+  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, p->pairs / (64ll << 20)));
+  std::vector<int64_t> b((size_t)nchunks + 1);
+  b[0] = p->row_begin;
+  const int64_t base = tri_strict_rows(p->n, p->row_begin);
+  int64_t r = p->row_begin;
+  for (int c = 1; c < nchunks; ++c) {
+    const int64_t target = base + p->pairs * c / nchunks;
+    while (r < p->row_end && tri_strict_rows(p->n, r) < target) ++r;
+    b[(size_t)c] = r;
+  }
+  b[(size_t)nchunks] = p->row_end;
+  DevBuf<uint8_t> d8;
+  DevBuf<long long> d_ei;
+  DevBuf<uint16_t> d_ec;
+  DevBuf<unsigned long long> d_en;
+  DYNA_TRY(d8.alloc((size_t)p->pairs));
+  DYNA_TRY(d_ei.alloc((size_t)std::max<int64_t>(esc_capacity, 1)));
+  DYNA_TRY(d_ec.alloc((size_t)std::max<int64_t>(esc_capacity, 1)));
+  DYNA_TRY(d_en.alloc(1));
+  DYNA_CUDA(cudaMemsetAsync(d_en.p, 0, sizeof(unsigned long long), st));
+  cudaStream_t copy_st;
+  DYNA_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+  std::vector<cudaEvent_t> ev((size_t)nchunks, nullptr);
+  int rc = DYNA_OK, launches = 0;
+  for (int c = 0; c < nchunks && rc == DYNA_OK; ++c) {
+    cudaEventCreateWithFlags(&ev[(size_t)c], cudaEventDisableTiming);
+    const int64_t r0 = b[(size_t)c], r1 = b[(size_t)c + 1];
+    if (r1 <= r0) continue;
+    const int64_t off = tri_strict_rows(p->n, r0) - base, cnt = tri_strict_rows(p->n, r1) - tri_strict_rows(p->n, r0);
+    int l = 0;
+    rc = launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, r0, r1, p->counts.p + off,
+                         p->use16 ? p->sigP.p : nullptr, p->use16 ? p->overflow.p : nullptr, st, &l);
+    launches += l;
+    if (rc == DYNA_OK)
+      rc = launch_mh_narrow8(p->counts.p + off, cnt, base + off, d8.p + off, esc_capacity, d_ei.p, d_ec.p, d_en.p, st);
+    ++launches;
+    if (rc != DYNA_OK) break;
+    cudaEventRecord(ev[(size_t)c], st);
+    cudaStreamWaitEvent(copy_st, ev[(size_t)c], 0);
+    if (cnt > 0 && cudaMemcpyAsync(counts8_out + off, d8.p + off, (size_t)cnt, cudaMemcpyDeviceToHost, copy_st) != cudaSuccess)
+      rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  unsigned long long n_esc = 0;
+  if (rc == DYNA_OK && cudaMemcpyAsync(&n_esc, d_en.p, sizeof n_esc, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: %s", cudaGetErrorString(cudaGetLastError()));
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaStreamSynchronize(copy_st) != cudaSuccess)
+    if (rc == DYNA_OK) rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == DYNA_OK) {
+    if (n_esc_out) *n_esc_out = (int64_t)n_esc;
+    if ((int64_t)n_esc > esc_capacity)
+      rc = fail(DYNA_ERR_INVALID, "escape buffer too small: %lld pairs have a count >= 255, capacity %lld", (long long)n_esc,
+                (long long)esc_capacity);
+    else if (n_esc > 0) {
+      static_assert(sizeof(long long) == sizeof(int64_t), "escape index type");
+      if (cudaMemcpy(esc_index_out, d_ei.p, sizeof(int64_t) * n_esc, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(esc_count_out, d_ec.p, sizeof(uint16_t) * n_esc, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(copy_st);
+  p->launches = launches;
+  return rc;
+}
+
 extern "C" int64_t dyna_mh_plan_pairs(const dyna_mh_plan* p) { return p ? p->pairs : 0; }
 extern "C" int dyna_mh_plan_launches(const dyna_mh_plan* p) { return p ? p->launches : 0; }
 extern "C" void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan* p) { return p ? p->counts.p : nullptr; }
@@ -843,6 +1015,47 @@ extern "C" int dyna_nw_plan_fetch(dyna_nw_plan* p, uint32_t* matches_out, uint32
   return DYNA_OK;
 }
 
+// Position-weighted checksums of the plan's (matches, length) slab: sum_out[0] over matches, sum_out[1] over length.
+extern "C" int dyna_nw_plan_checksum(dyna_nw_plan* p, uint64_t* sum_out, void* stream) {
+  if (!p || !sum_out) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_checksum: null argument");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  DevBuf<unsigned long long> d_sum;
+  DYNA_TRY(d_sum.alloc(2));
+  const int64_t first = tri_diag_rows(p->n, p->row_begin);
+  DYNA_TRY(launch_checksum_u32(p->matches.p, p->pairs, first, d_sum.p, st));
+  DYNA_TRY(launch_checksum_u32(p->length.p, p->pairs, first, d_sum.p + 1, st));
+  unsigned long long h[2] = {0, 0};
+  DYNA_CUDA(cudaMemcpyAsync(h, d_sum.p, sizeof h, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  sum_out[0] = h[0];
+  sum_out[1] = h[1];
+  return DYNA_OK;
+}
+
+// fetch in the narrow host form: one byte for matches and one for the alignment length per pair (2 B/pair instead of
+// 8).  Only for plans whose every alignment length fits a byte: max_len_i + max_len_j <= 255 (short peptides -- the
+// 100,000 x 16-mer target is 10 GB this way instead of 40 GB).
+extern "C" int dyna_nw_plan_fetch_packed8(dyna_nw_plan* p, uint8_t* matches8_out, uint8_t* length8_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (2 * (int64_t)p->max_cols > 255)
+    return fail(DYNA_ERR_UNSUPPORTED, "dyna_nw_plan_fetch_packed8: alignment lengths up to %lld do not fit one byte",
+                2 * (long long)p->max_cols);
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  if (p->pairs <= 0) return DYNA_OK;
+  DevBuf<uint8_t> m8, l8;
+  DYNA_TRY(m8.alloc((size_t)p->pairs));
+  DYNA_TRY(l8.alloc((size_t)p->pairs));
+  DYNA_TRY(launch_nw_pack8(p->matches.p, p->length.p, p->pairs, m8.p, l8.p, st));
+  DYNA_CUDA(cudaMemcpyAsync(matches8_out, m8.p, (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaMemcpyAsync(length8_out, l8.p, (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
 extern "C" int64_t dyna_nw_plan_pairs(const dyna_nw_plan* p) { return p ? p->pairs : 0; }
 extern "C" int64_t dyna_nw_plan_cells(const dyna_nw_plan* p) { return p ? p->cells : 0; }
 extern "C" int dyna_nw_plan_launches(const dyna_nw_plan* p) { return p ? p->launches : 0; }
@@ -864,6 +1077,16 @@ extern "C" int dyna_device_count(void) {
     return 0;
   }
   return count;
+}
+// Device memory of finished calls stays cached in the stream-ordered pool (see common.cuh); this hands it back to
+// the driver, e.g. before another process or another phase needs the device's memory.
+extern "C" int dyna_release_cached_memory(int device) {
+  DYNA_TRY(use_device(device));
+  DYNA_CUDA(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  DYNA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  DYNA_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return DYNA_OK;
 }
 extern "C" int dyna_set_device(int device) {
   DYNA_TRY(use_device(device));
@@ -993,72 +1216,64 @@ void mh_value_table(int n_hash, int kind, std::vector<double>& table, double* di
   *diag = (kind == DYNA_MH_DISTANCE) ? 0.0 : 1.0;
 }
 
-// host-side scatter of a counts slab (used when several GPUs each own a row block)
-void mh_expand_host(const uint16_t* counts, int64_t n, int64_t row_begin, int64_t row_end, const std::vector<double>& table,
-                    double diag, double* out) {
-  const int64_t base = tri_strict_rows(n, row_begin);
-  for (int64_t i = row_begin; i < row_end; ++i) {
-    out[i + i * n] = diag;
-    const uint16_t* row = counts + (tri_strict_rows(n, i) - base) - (i + 1);
-    for (int64_t j = i + 1; j < n; ++j) {
-      const double v = table[row[j]];
-      out[i + j * n] = v;
-      out[j + i * n] = v;
-    }
-  }
-}
-
-// one GPU: plan over all rows with signatures already resident -> expanded matrix to host
-int mh_matrix_single(dyna_mh_plan* p, int kind, double* out) {
-  std::vector<double> table;
-  double diag;
-  mh_value_table(p->n_hash, kind, table, &diag);
-  DevBuf<double> d_table, d_out;
-  DYNA_TRY(d_table.alloc(table.size()));
-  DYNA_TRY(d_out.alloc((size_t)p->n * p->n));
-  DYNA_CUDA(cudaMemcpy(d_table.p, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
-  DYNA_TRY(dyna_mh_plan_run_match(p, nullptr));
-  DYNA_TRY(launch_mh_expand(p->counts.p, p->n, p->row_begin, p->row_end, d_table.p, diag, d_out.p, nullptr));
-  DYNA_CUDA(cudaMemcpy(out, d_out.p, sizeof(double) * (size_t)p->n * p->n, cudaMemcpyDeviceToHost));
-  return DYNA_OK;
-}
-
-// several GPUs from one process: one host thread per device, each owning a balanced row block; slabs are gathered
-// to the host and scattered there.  prepare(plan) must leave signatures resident on that plan's device.
+// The n x n double matrix from `gpus` devices of this process (gpus == 1 included).  Device g matches its pair-
+// balanced row block; after all devices have finished, device g expands COLUMNS [n*g/G, n*(g+1)/G) -- reading every
+// slab those columns need out of the owning device's memory (peer loads over NVLink) -- and copies its block, a
+// contiguous range of the caller's matrix, to the host.  prepare(plan) must leave signatures resident on the plan's
+// device.  No slab is staged through the host and the host does no arithmetic.
 template <class Prepare>
-int mh_matrix_multi(int64_t n, int n_hash, int kind, int gpus, double* out, Prepare prepare) {
-  std::vector<int64_t> bounds((size_t)gpus + 1);
+int mh_matrix_gpus(int64_t n, int n_hash, int kind, int gpus, double* out, Prepare prepare) {
+  if (gpus > kMaxSlabs) gpus = kMaxSlabs;
+  if (gpus > 1 && !enable_peer_mesh(gpus)) gpus = 1;  // no peer access between the devices: one device does it all
+  const int dev0 = g_device;
+  std::vector<int64_t> bounds((size_t)gpus + 1), cols;
   DYNA_TRY(dyna_partition_rows(n, nullptr, 0, gpus, bounds.data()));
+  column_blocks(n, gpus, cols);
   std::vector<double> table;
   double diag;
   mh_value_table(n_hash, kind, table, &diag);
-  std::vector<int> rcs((size_t)gpus, DYNA_OK);
-  std::vector<std::string> errs((size_t)gpus);
-  std::vector<std::thread> th;
-  for (int g = 0; g < gpus; ++g)
-    th.emplace_back([&, g]() {
-      int rc = DYNA_OK;
-      dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, bounds[(size_t)g], bounds[(size_t)g + 1], g);
-      if (!p) rc = DYNA_ERR_CUDA;
-      std::vector<uint16_t> slab;
-      if (rc == DYNA_OK) rc = prepare(p);
-      if (rc == DYNA_OK) rc = dyna_mh_plan_run_match(p, nullptr);
-      if (rc == DYNA_OK) {
-        slab.resize((size_t)std::max<int64_t>(p->pairs, 1));
-        rc = dyna_mh_plan_fetch_counts(p, slab.data(), nullptr);
-      }
-      if (rc == DYNA_OK) mh_expand_host(slab.data(), n, p->row_begin, p->row_end, table, diag, out);
-      if (rc != DYNA_OK) errs[(size_t)g] = err_slot();
-      rcs[(size_t)g] = rc;
-      dyna_mh_plan_destroy(p);
-    });
-  for (auto& t : th) t.join();
-  for (int g = 0; g < gpus; ++g)
-    if (rcs[(size_t)g] != DYNA_OK) {
-      err_slot() = errs[(size_t)g];
-      return rcs[(size_t)g];
+  std::vector<dyna_mh_plan*> plans((size_t)gpus, nullptr);
+  auto device_of = [&](int g) { return gpus == 1 ? dev0 : g; };
+  int rc = for_each_gpu(gpus, [&](int g) {
+    DYNA_TRY(use_device(device_of(g)));
+    const int64_t cb = cols[(size_t)g + 1] - cols[(size_t)g];
+    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)cb + 2.0 * (double)(tri_strict_rows(n, bounds[(size_t)g + 1]) -
+                                                                          tri_strict_rows(n, bounds[(size_t)g])),
+                               device_of(g), "the n x n double matrix"));
+    plans[(size_t)g] = dyna_mh_plan_create(n, n_hash, bounds[(size_t)g], bounds[(size_t)g + 1], device_of(g));
+    if (!plans[(size_t)g]) return plan_error_code_mh();
+    DYNA_TRY(prepare(plans[(size_t)g]));
+    DYNA_TRY(dyna_mh_plan_run_match(plans[(size_t)g], nullptr));
+    DYNA_CUDA(cudaStreamSynchronize(nullptr));  // this slab is complete before any device starts to read it
+    return (int)DYNA_OK;
+  });
+  if (rc == DYNA_OK) {
+    TriSlabs slabs{};
+    slabs.nslabs = gpus;
+    for (int g = 0; g < gpus; ++g) {
+      slabs.row_begin[g] = bounds[(size_t)g];
+      slabs.a[g] = plans[(size_t)g]->counts.p;
+      slabs.b[g] = nullptr;
     }
-  return DYNA_OK;
+    slabs.row_begin[gpus] = n;
+    rc = for_each_gpu(gpus, [&](int g) {
+      DYNA_TRY(use_device(device_of(g)));
+      const int64_t c0 = cols[(size_t)g], c1 = cols[(size_t)g + 1];
+      if (c1 <= c0) return (int)DYNA_OK;
+      DevBuf<double> d_table, d_block;
+      DYNA_TRY(d_table.alloc(table.size()));
+      DYNA_TRY(d_block.alloc((size_t)n * (size_t)(c1 - c0)));
+      DYNA_CUDA(cudaMemcpyAsync(d_table.p, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice, nullptr));
+      DYNA_TRY(launch_mh_expand_block(slabs, n, c0, c1, d_table.p, diag, d_block.p, nullptr));
+      DYNA_CUDA(cudaMemcpyAsync(out + c0 * n, d_block.p, sizeof(double) * (size_t)n * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, nullptr));
+      DYNA_CUDA(cudaStreamSynchronize(nullptr));
+      return (int)DYNA_OK;
+    });
+  }
+  for (int g = 0; g < gpus; ++g)
+    if (plans[(size_t)g]) dyna_mh_plan_destroy(plans[(size_t)g]);
+  if (gpus > 1) cudaSetDevice(dev0);
+  return rc;
 }
 
 }  // namespace
@@ -1071,19 +1286,8 @@ extern "C" int dyna_mh_match_matrix(const uint32_t* sig, int64_t n, int n_hash, 
   int gpus = 1;
   DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
   if (n < 2 * 128 * gpus) gpus = 1;
-  if (gpus == 1) {
-    DYNA_TRY(use_device(g_device));
-    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)n + 2.0 * (double)tri_strict_rows(n, n), g_device,
-                               "dyna_mh_match_matrix: the n x n double matrix"));
-    dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
-    if (!p) return plan_error_code_mh();
-    int rc = dyna_mh_plan_upload_signatures(p, sig, nullptr);
-    if (rc == DYNA_OK) rc = mh_matrix_single(p, kind, out);
-    dyna_mh_plan_destroy(p);
-    return rc;
-  }
-  return mh_matrix_multi(n, n_hash, kind, gpus, out,
-                         [&](dyna_mh_plan* p) { return dyna_mh_plan_upload_signatures(p, sig, nullptr); });
+  return mh_matrix_gpus(n, n_hash, kind, gpus, out,
+                        [&](dyna_mh_plan* p) { return dyna_mh_plan_upload_signatures(p, sig, nullptr); });
 }
 
 extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets, int64_t n, int k, int n_hash,
@@ -1104,24 +1308,7 @@ extern "C" int dyna_similarityMH(const uint8_t* residues, const int64_t* offsets
     if (rc == DYNA_OK) rc = dyna_mh_plan_run_signatures(p, nullptr);  // every GPU rebuilds all signatures (< 1 ms)
     return rc;
   };
-  if (gpus == 1) {
-    PhaseTimer tm;
-    DYNA_TRY(use_device(g_device));
-    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)n + 2.0 * (double)tri_strict_rows(n, n), g_device,
-                               "similarityMH: the n x n double matrix"));
-    dyna_mh_plan* p = dyna_mh_plan_create(n, n_hash, 0, n, g_device);
-    if (!p) return plan_error_code_mh();
-    tm.lap("mh plan create");
-    int rc = prepare(p);
-    if (tm.on) cudaDeviceSynchronize();
-    tm.lap("mh upload + signatures");
-    if (rc == DYNA_OK) rc = mh_matrix_single(p, DYNA_MH_SIMILARITY, out);
-    tm.lap("mh match + expand + D2H");
-    dyna_mh_plan_destroy(p);
-    tm.lap("mh plan destroy");
-    return rc;
-  }
-  return mh_matrix_multi(n, n_hash, DYNA_MH_SIMILARITY, gpus, out, prepare);
+  return mh_matrix_gpus(n, n_hash, DYNA_MH_SIMILARITY, gpus, out, prepare);
 }
 
 // =====================================================================================================
@@ -1144,18 +1331,19 @@ extern "C" int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offset
   return rc;
 }
 
-namespace {
-void nw_expand_host(const uint32_t* matches, const uint32_t* length, int64_t n, int64_t row_begin, int64_t row_end, double* out) {
-  const int64_t base = tri_diag_rows(n, row_begin);
-  for (int64_t i = row_begin; i < row_end; ++i) {
-    const int64_t rb = tri_diag_rows(n, i) - base - i;
-    for (int64_t j = i; j < n; ++j) {
-      const double v = static_cast<double>(matches[rb + j]) / static_cast<double>(length[rb + j]);  // 0/0 -> NaN
-      out[i + j * n] = v;
-      out[j + i * n] = v;
-    }
-  }
+// dyna_nw_pair_stats with the narrow result form of dyna_nw_plan_fetch_packed8 (2 bytes per pair)
+extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                                   int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint8_t* matches8_out,
+                                   uint8_t* length8_out) {
+  dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, g_device);
+  if (!p) return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA;
+  int rc = dyna_nw_plan_run(p, nullptr);
+  if (rc == DYNA_OK) rc = dyna_nw_plan_fetch_packed8(p, matches8_out, length8_out, nullptr);
+  dyna_nw_plan_destroy(p);
+  return rc;
 }
+
+namespace {
 int plan_error_code() { return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA; }  // code of the failed plan creation
 }  // namespace
 
@@ -1173,54 +1361,55 @@ extern "C" int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets
   DYNA_TRY(validate_residues(residues, offsets, n));
   DYNA_TRY(resolve_gpus(n_gpus == 0 ? 1 : n_gpus, &gpus));
   if (n < 64 * gpus) gpus = 1;
-  if (gpus == 1) {
-    DYNA_TRY(use_device(g_device));
-    // n x n doubles plus the (matches, length) slab of the whole triangle
-    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)n + 8.0 * (double)tri_diag_rows(n, n), g_device,
-                               "similarityNW: the n x n double matrix"));
-    dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, 0, n, g_device);
-    if (!p) return plan_error_code();
-    int rc = dyna_nw_plan_run(p, nullptr);
-    if (rc == DYNA_OK) {
-      DevBuf<double> d_out;
-      rc = d_out.alloc((size_t)n * n);
-      if (rc == DYNA_OK) rc = launch_nw_expand(p->matches.p, p->length.p, n, 0, n, d_out.p, nullptr);
-      if (rc == DYNA_OK && cudaMemcpy(out, d_out.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost) != cudaSuccess)
-        rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    dyna_nw_plan_destroy(p);
-    return rc;
-  }
-  // several GPUs: row blocks balanced by DP cells (len_i * len_j), one host thread per device, host-side scatter
-  std::vector<int64_t> lens((size_t)n), bounds((size_t)gpus + 1);
+  // Row blocks balanced by DP cells (len_i * len_j), one host thread per device.  When every device has finished its
+  // block, device g expands columns [n*g/G, n*(g+1)/G) of the result -- gathering the (matches, length) entries those
+  // columns need from the other devices' slabs by peer loads over NVLink -- and copies its block, a contiguous range
+  // of the caller's column-major matrix, to the host (src/pairwiseSeqAlign.cpp:349-350 writes both triangles).
+  if (gpus > kMaxSlabs) gpus = kMaxSlabs;
+  if (gpus > 1 && !enable_peer_mesh(gpus)) gpus = 1;
+  const int dev0 = g_device;
+  auto device_of = [&](int g) { return gpus == 1 ? dev0 : g; };
+  std::vector<int64_t> lens((size_t)n), bounds((size_t)gpus + 1), cols;
   for (int64_t i = 0; i < n; ++i) lens[(size_t)i] = offsets[i + 1] - offsets[i];
   DYNA_TRY(dyna_partition_rows(n, lens.data(), 1, gpus, bounds.data()));
-  std::vector<int> rcs((size_t)gpus, DYNA_OK);
-  std::vector<std::string> errs((size_t)gpus);
-  std::vector<std::thread> th;
-  for (int g = 0; g < gpus; ++g)
-    th.emplace_back([&, g]() {
-      int rc = DYNA_OK;
-      dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, bounds[(size_t)g],
-                                            bounds[(size_t)g + 1], g);
-      if (!p) rc = plan_error_code();
-      std::vector<uint32_t> mt, ln;
-      if (rc == DYNA_OK) rc = dyna_nw_plan_run(p, nullptr);
-      if (rc == DYNA_OK) {
-        mt.resize((size_t)std::max<int64_t>(p->pairs, 1));
-        ln.resize((size_t)std::max<int64_t>(p->pairs, 1));
-        rc = dyna_nw_plan_fetch(p, mt.data(), ln.data(), nullptr);
-      }
-      if (rc == DYNA_OK) nw_expand_host(mt.data(), ln.data(), n, p->row_begin, p->row_end, out);
-      if (rc != DYNA_OK) errs[(size_t)g] = err_slot();
-      rcs[(size_t)g] = rc;
-      dyna_nw_plan_destroy(p);
-    });
-  for (auto& t : th) t.join();
-  for (int g = 0; g < gpus; ++g)
-    if (rcs[(size_t)g] != DYNA_OK) {
-      err_slot() = errs[(size_t)g];
-      return rcs[(size_t)g];
+  column_blocks(n, gpus, cols);
+  std::vector<dyna_nw_plan*> plans((size_t)gpus, nullptr);
+  int rc = for_each_gpu(gpus, [&](int g) {
+    DYNA_TRY(use_device(device_of(g)));
+    const int64_t cb = cols[(size_t)g + 1] - cols[(size_t)g];
+    DYNA_TRY(check_device_fits(8.0 * (double)n * (double)cb + 8.0 * (double)(tri_diag_rows(n, bounds[(size_t)g + 1]) -
+                                                                          tri_diag_rows(n, bounds[(size_t)g])),
+                               device_of(g), "similarityNW: the n x n double matrix"));
+    plans[(size_t)g] = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, bounds[(size_t)g],
+                                           bounds[(size_t)g + 1], device_of(g));
+    if (!plans[(size_t)g]) return plan_error_code();
+    DYNA_TRY(dyna_nw_plan_run(plans[(size_t)g], nullptr));
+    DYNA_CUDA(cudaStreamSynchronize(nullptr));  // this slab is complete before any device starts to read it
+    return (int)DYNA_OK;
+  });
+  if (rc == DYNA_OK) {
+    TriSlabs slabs{};
+    slabs.nslabs = gpus;
+    for (int g = 0; g < gpus; ++g) {
+      slabs.row_begin[g] = bounds[(size_t)g];
+      slabs.a[g] = plans[(size_t)g]->matches.p;
+      slabs.b[g] = plans[(size_t)g]->length.p;
     }
-  return DYNA_OK;
+    slabs.row_begin[gpus] = n;
+    rc = for_each_gpu(gpus, [&](int g) {
+      DYNA_TRY(use_device(device_of(g)));
+      const int64_t c0 = cols[(size_t)g], c1 = cols[(size_t)g + 1];
+      if (c1 <= c0) return (int)DYNA_OK;
+      DevBuf<double> d_block;
+      DYNA_TRY(d_block.alloc((size_t)n * (size_t)(c1 - c0)));
+      DYNA_TRY(launch_nw_expand_block(slabs, n, c0, c1, d_block.p, nullptr));
+      DYNA_CUDA(cudaMemcpyAsync(out + c0 * n, d_block.p, sizeof(double) * (size_t)n * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, nullptr));
+      DYNA_CUDA(cudaStreamSynchronize(nullptr));
+      return (int)DYNA_OK;
+    });
+  }
+  for (int g = 0; g < gpus; ++g)
+    if (plans[(size_t)g]) dyna_nw_plan_destroy(plans[(size_t)g]);
+  if (gpus > 1) cudaSetDevice(dev0);
+  return rc;
 }

@@ -7,7 +7,7 @@
 //   mh_transpose_kernel              row-major -> hash-major layout for the match kernel
 //   K3 mh_match_kernel               counts[i][j] = #{h : sig[i][h]==sig[j][h]}, strict upper triangle
 //                                    (reference: src/minHash.cpp:160-173, R/minHash.R:171-176)
-//   mh_expand_kernel                 counts -> column-major doubles, both triangles + diagonal
+//   (expansion to the column-major double matrix: gather.cu)
 //                                    (reference: src/minHash.cpp:161,174-176; R/minHash.R:175-176)
 //
 // None of this is a dense contraction (the "multiply" is ==), so no tensor cores: the match kernel is an
@@ -652,28 +652,6 @@ mh_rank_scatter_kernel(const uint32_t* __restrict__ keys_sorted, const uint32_t*
   if (threadIdx.x == 0 && running > max_codes) atomicExch(overflow, 1);
 }
 
-// ------------------------------------------------------------------------------------------------
-// expansion of a counts slab into the R matrix: value table lookup (host computes the n_hash+1 doubles
-// with the reference's exact arithmetic, incl. R's long-double mean())
-// ------------------------------------------------------------------------------------------------
-__global__ void mh_expand_kernel(const uint16_t* __restrict__ counts, int64_t n, int64_t row_begin, int64_t row_end,
-                                 int64_t slab_base, const double* __restrict__ table, double diag,
-                                 double* __restrict__ out) {
-  // one block row per matrix row i; threads over j
-  for (int64_t i = row_begin + blockIdx.y; i < row_end; i += gridDim.y) {
-    const int64_t rowbase = i * n - i * (i + 1) / 2 - i - 1 - slab_base;
-    for (int64_t j = i + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-      if (j == i) {
-        out[i + i * n] = diag;
-      } else {
-        const double v = table[counts[rowbase + j]];
-        out[i + j * n] = v;
-        out[j + i * n] = v;
-      }
-    }
-  }
-}
-
 // gather of signature rows for a sub-cluster (clusterbreak re-invokes sim_fn on subsets, R/clusterbreak.R:250-254):
 // the signatures of a subset are the subset of the signatures, so nothing is re-hashed
 __global__ void mh_gather_rows_kernel(const uint32_t* __restrict__ sig, const int64_t* __restrict__ idx, int64_t m, int n_hash,
@@ -961,16 +939,6 @@ int launch_mh_match(const uint32_t* d_sigT, int64_t npitch, int hrows, int n_has
   DYNA_CUDA(cudaGetLastError());
   ++nl;
   if (launches) *launches = nl;
-  return DYNA_OK;
-}
-
-int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,
-                     double diag, double* d_out, cudaStream_t st) {
-  if (row_end <= row_begin) return DYNA_OK;
-  const int64_t slab_base = tri_strict_rows(n, row_begin);
-  dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)std::min<int64_t>(row_end - row_begin, 32768));
-  mh_expand_kernel<<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, slab_base, d_table, diag, d_out);
-  DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }
 

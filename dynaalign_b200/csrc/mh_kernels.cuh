@@ -49,11 +49,6 @@ size_t mh_relabel_temp_bytes(int64_t npitch, int hrows);
 int launch_mh_iota(uint32_t* d_vals, int64_t npitch, int rows, cudaStream_t st);
 int launch_mh_relabel(const uint32_t* d_sigT, int64_t n, int n_hash, int64_t npitch, int hrows, const MhRelabelWork& w,
                       int code_row_begin, int code_row_end, cudaStream_t st, int* launches);
-// expand a counts slab into the column-major double matrix (both triangles + diagonal of the slab's rows):
-// out = table[count]; the n_hash+1 table entries are computed on the host with the reference's arithmetic
-int launch_mh_expand(const uint16_t* d_counts, int64_t n, int64_t row_begin, int64_t row_end, const double* d_table,
-                     double diag, double* d_out, cudaStream_t st);
-
 int launch_mh_gather_rows(const uint32_t* d_sig, const int64_t* d_idx, int64_t m, int n_hash, uint32_t* d_out, cudaStream_t st);
 // threshold + sparsify (R/clusterbreak.R:219-221) on the counts slab
 int launch_mh_count_hist(const uint16_t* d_counts, int64_t total, int n_hash, unsigned long long* d_hist, cudaStream_t st);

@@ -1420,19 +1420,6 @@ __global__ void nw_empty_rows_kernel(NwDeviceData d, const NwUnit* __restrict__ 
   }
 }
 
-__global__ void nw_expand_kernel(const uint32_t* __restrict__ matches, const uint32_t* __restrict__ length, int64_t n,
-                                 int64_t row_begin, int64_t row_end, int64_t slab_base, double* __restrict__ out) {
-  for (int64_t i = row_begin + blockIdx.y; i < row_end; i += gridDim.y) {
-    const int64_t rowbase = i * n - i * (i - 1) / 2 - i - slab_base;  // + j
-    for (int64_t j = i + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-      // static_cast<double>(matches) / alignment_length (src/pairwiseSeqAlign.cpp:311); IEEE double divide, 0/0 = NaN
-      const double v = __ddiv_rn((double)matches[rowbase + j], (double)length[rowbase + j]);
-      out[i + j * n] = v;
-      out[j + i * n] = v;
-    }
-  }
-}
-
 template <int R>
 int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   if (slant) nw_warp_kernel<R, true, false><<<num_units, kWarpThreads, 0, st>>>(d, d_units, num_units, nullptr, 0);
@@ -1608,16 +1595,6 @@ int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw warp2 kernel: unsupported strip height %d", R);
   }
-}
-
-int launch_nw_expand(const uint32_t* d_matches, const uint32_t* d_length, int64_t n, int64_t row_begin, int64_t row_end,
-                     double* d_out, cudaStream_t st) {
-  if (row_end <= row_begin) return DYNA_OK;
-  const int64_t slab_base = tri_diag_rows(n, row_begin);
-  dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)std::min<int64_t>(row_end - row_begin, 32768));
-  nw_expand_kernel<<<grid, 256, 0, st>>>(d_matches, d_length, n, row_begin, row_end, slab_base, d_out);
-  DYNA_CUDA(cudaGetLastError());
-  return DYNA_OK;
 }
 
 }  // namespace dyna

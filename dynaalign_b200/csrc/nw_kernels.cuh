@@ -61,8 +61,4 @@ inline int nw_co_R(int m) { return (m + 63) / 64; }
 int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 constexpr int kNwWarp2MpMaxRows = 32 * 12 * 8;  // 8 passes at most
 constexpr int kNwWarp2MpMaxCols = 2048;        // its column-sequence limit (staging buffer)
-// (matches, length) slab -> column-major doubles, both triangles (reference: src/pairwiseSeqAlign.cpp:311,349-350)
-int launch_nw_expand(const uint32_t* d_matches, const uint32_t* d_length, int64_t n, int64_t row_begin, int64_t row_end,
-                     double* d_out, cudaStream_t st);
-
 }  // namespace dyna

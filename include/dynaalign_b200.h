@@ -32,8 +32,10 @@
  *     argument errors the message is byte-identical to the reference's Rcpp::stop() text so the R side can
  *     re-raise it unchanged.  There is NO CPU fallback: without a usable CUDA device every compute entry
  *     point fails with DYNA_ERR_CUDA.
- *   - n_gpus: number of devices one call may drive from this process (row blocks balanced by work);
- *     values <= 0 mean "all visible".  Multi-process launches (one rank per GPU) use the row-range entry
+ *   - n_gpus: number of devices one call may drive from this process (row blocks balanced by work, one host thread
+ *     per device).  The n x n matrix is then assembled in column blocks: every device expands its share of the
+ *     columns, reading the result slabs of the other devices by peer loads over NVLink, and copies that contiguous
+ *     block to the caller's matrix.  Values <= 0 mean "all visible".  Multi-process launches (one rank per GPU) use the row-range entry
  *     points with dyna_partition_rows instead.
  *   - Thread safety: calls are serialised per device internally; the API is re-entrant across devices.
  */
@@ -66,6 +68,9 @@ DYNA_API const char* dyna_last_error(void);
 DYNA_API int dyna_version(void);
 DYNA_API int dyna_device_count(void); /* 0 when no usable device; never fails */
 DYNA_API int dyna_set_device(int device); /* device used by single-GPU entry points of this thread (default 0) */
+/* Device buffers of finished calls stay cached in the CUDA memory pool for the next call (clusterbreak calls sim_fn
+ * once per recursion node); this returns the cached memory of `device` to the driver. */
+DYNA_API int dyna_release_cached_memory(int device);
 
 /* Balanced row partition of the upper triangle.  weights==NULL: every pair costs 1
  * (MinHash); otherwise pair (i,j) costs weights[i]*weights[j] (NW: sequence lengths -> DP cells).
@@ -123,6 +128,11 @@ DYNA_API int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offsets,
                        int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint32_t* matches_tri_out,
                        uint32_t* length_tri_out);
 
+/* dyna_nw_pair_stats in the narrow form of dyna_nw_plan_fetch_packed8 (short peptides: 2 bytes per pair). */
+DYNA_API int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                        int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint8_t* matches8_tri_out,
+                        uint8_t* length8_tri_out);
+
 /* Drop-in for similarityNW(sequences, matrixName, gapOpen, gapExt). n==0 -> OK, nothing written (0x0 matrix). */
 DYNA_API int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
                       int gap_open, int gap_ext, double* out_colmajor, int n_gpus);
@@ -172,6 +182,15 @@ DYNA_API int dyna_mh_plan_count_histogram(dyna_mh_plan*, uint64_t* hist_out /* n
 DYNA_API int dyna_quantile_type7_counts(const uint64_t* hist, int n_hash, double prob, double* threshold_out, int* min_count_out);
 DYNA_API int dyna_mh_plan_threshold_edges(dyna_mh_plan*, int min_count, int64_t max_edges, int32_t* i_out, int32_t* j_out,
                                  uint16_t* count_out, int64_t* n_edges_out, void* stream);
+/* run_match_fetch in the narrow host form (1 byte per pair instead of 2): counts8_out holds min(count, 255) and every
+ * pair with count >= 255 is also reported exactly as (packed pair index in the FULL strict triangle, count) -- lossless.
+ * Escapes arrive unordered; more than esc_capacity of them fails with DYNA_ERR_INVALID and *n_esc_out = the number. */
+DYNA_API int dyna_mh_plan_run_match_fetch8(dyna_mh_plan*, uint8_t* counts8_out, int64_t esc_capacity, int64_t* esc_index_out,
+                                  uint16_t* esc_count_out, int64_t* n_esc_out, void* stream);
+/* sum over the plan's slab of count[k] * w(global pair index k), w(k) = x ^ (x >> 31), x = (k+1)*0x9E3779B97F4A7C15,
+ * in wrap-around 64-bit arithmetic.  Additive over the slabs of any row partition: summed over all ranks it equals
+ * the single-device value exactly when the slabs tile the triangle (bench.py's multi-GPU parity check). */
+DYNA_API int dyna_mh_plan_checksum(dyna_mh_plan*, uint64_t* sum_out /* 1 */, void* stream);
 DYNA_API int64_t dyna_mh_plan_pairs(const dyna_mh_plan*);
 DYNA_API int dyna_mh_plan_launches(const dyna_mh_plan*); /* kernels enqueued by the last run_* call */
 DYNA_API void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan*);
@@ -182,6 +201,11 @@ DYNA_API dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int64_
                                   int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, int device);
 DYNA_API int dyna_nw_plan_run(dyna_nw_plan*, void* stream);
 DYNA_API int dyna_nw_plan_fetch(dyna_nw_plan*, uint32_t* matches_tri_out, uint32_t* length_tri_out, void* stream);
+/* Narrow host form: one byte each for matches and alignment length (2 B/pair instead of 8).  Only when every
+ * alignment length fits a byte (2 * longest sequence <= 255); DYNA_ERR_UNSUPPORTED otherwise. */
+DYNA_API int dyna_nw_plan_fetch_packed8(dyna_nw_plan*, uint8_t* matches8_tri_out, uint8_t* length8_tri_out, void* stream);
+/* Same weighting as dyna_mh_plan_checksum over the NW triangle (diagonal included): sum_out[0] matches, [1] length. */
+DYNA_API int dyna_nw_plan_checksum(dyna_nw_plan*, uint64_t* sum_out /* 2 */, void* stream);
 DYNA_API int64_t dyna_nw_plan_pairs(const dyna_nw_plan*);
 DYNA_API int64_t dyna_nw_plan_cells(const dyna_nw_plan*); /* sum of len_i*len_j over the plan's pairs */
 DYNA_API int dyna_nw_plan_launches(const dyna_nw_plan*);

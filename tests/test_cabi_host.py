@@ -167,3 +167,31 @@ def test_fasta_reader(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         read_fasta(bad)
+
+
+def test_offsets_must_be_non_decreasing():
+    # foreign callers hand in offsets[]: a decreasing or negative entry is an argument error, raised before any device work
+    L = _lib.lib()
+    res = np.frombuffer(b"ARNDARND", dtype=np.uint8).copy()
+    out = np.zeros(9, dtype=np.float64)
+    for bad in ([0, 5, 3, 8], [-1, 2, 4, 8], [0, 9, 8, 8]):
+        off = np.array(bad, dtype=np.int64)
+        rc = L.dyna_similarityNW(_lib.ptr(res, C.c_uint8), _lib.ptr(off, C.c_int64), 3, b"BLOSUM62", 10, 4, _lib.ptr(out, C.c_double), 1)
+        assert rc == _lib.ERR_INVALID and "offsets" in _lib.last_error()
+        seeds = np.zeros(4, dtype=np.uint32)
+        rc = L.dyna_similarityMH(_lib.ptr(res, C.c_uint8), _lib.ptr(off, C.c_int64), 3, 2, 4, _lib.ptr(seeds, C.c_uint32),
+                                 _lib.ptr(out, C.c_double), 1)
+        assert rc == _lib.ERR_INVALID and "offsets" in _lib.last_error()
+        assert not L.dyna_nw_plan_create(_lib.ptr(res, C.c_uint8), _lib.ptr(off, C.c_int64), 3, b"BLOSUM62", 10, 4, 0, 3, 0)
+        assert "offsets" in _lib.last_error()
+
+
+def test_checksum_restatement_is_position_weighted():
+    import dynaalign_b200 as da
+    v = np.array([3, 1, 4, 1, 5, 9, 2, 6], dtype=np.uint32)
+    whole = da.checksum(v)
+    assert whole == (da.checksum(v[:3]) + da.checksum(v[3:], 3)) % (1 << 64)   # additive over slabs at their global offsets
+    assert whole != (da.checksum(v[:3]) + da.checksum(v[3:], 4)) % (1 << 64)   # ... and only there
+    assert da.checksum(v) != da.checksum(v[::-1].copy())                        # order matters
+    w = da.checksum_weights(0, 2)
+    assert int(w[0]) == (0x9E3779B97F4A7C15 ^ (0x9E3779B97F4A7C15 >> 31))

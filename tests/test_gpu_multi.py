@@ -1,9 +1,13 @@
-"""GPU, >= 2 devices: one process driving several GPUs through the host entry points (row blocks, one host thread
-per device, host-side scatter) gives bit-identical matrices to the single-GPU run."""
+"""GPU, >= 2 devices.  One process driving several GPUs through the R-facing entry points (row blocks, one host
+thread per device, column blocks of the result gathered from the other devices' slabs by peer loads) and one process
+per GPU over NCCL -- every result is compared with the ORACLE (the C port pinned to the compiled reference), not with
+another GPU run."""
+import numpy as np
 import pytest
 
 import dynaalign_b200 as da
 from dynaalign_b200 import _lib, synth
+from oracle import port
 
 pytestmark = pytest.mark.gpu
 
@@ -13,20 +17,42 @@ def _need2():
         pytest.skip("needs 2 CUDA devices")
 
 
-def test_similarityNW_two_gpus_identical():
+def test_similarityNW_two_gpus_equals_oracle():
     _need2()
-    seqs = [s.decode() for s in synth.proteins_families(260)]
-    a = da.similarityNW(seqs, n_gpus=1)
-    b = da.similarityNW(seqs, n_gpus=2)
-    assert a.tobytes(order="F") == b.tobytes(order="F")
+    # 200 related proteins of ~330 aa plus the shapes that change kernel class (short, empty, > 384 rows)
+    seqs = [s.decode() for s in synth.proteins_families(200)]
+    rng = np.random.default_rng(5)
+    al = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
+    seqs += [al[rng.integers(0, 20, size=int(L))].tobytes().decode() for L in (0, 7, 12, 31, 33, 400, 566, 700)]
+    want = port.similarityNW(seqs)
+    got2 = da.similarityNW(seqs, n_gpus=2)
+    assert got2.tobytes(order="F") == want.tobytes(order="F")
+    got1 = da.similarityNW(seqs, n_gpus=1)
+    assert got1.tobytes(order="F") == want.tobytes(order="F")
 
 
-def test_similarityMH_two_gpus_identical():
+def test_similarityMH_two_gpus_equals_oracle():
     _need2()
-    peps = [s.decode() for s in synth.peptides_clustered(3000, children=20)]
-    a = da.similarityMH(peps, 4, 100, seed=42, n_gpus=1)
-    b = da.similarityMH(peps, 4, 100, seed=42, n_gpus=2)
-    assert a.tobytes(order="F") == b.tobytes(order="F")
+    peps = [s.decode() for s in synth.peptides_clustered(1500, children=20)] + ["", "AC", "ACD"]
+    want = port.similarityMH(peps, 4, 100, 42)
+    got = da.similarityMH(peps, 4, 100, seed=42, n_gpus=2)
+    assert got.tobytes(order="F") == want.tobytes(order="F")
+
+
+def test_minhash_r_distance_two_gpus_equals_oracle():
+    _need2()
+    # the R pipeline's distance matrix (1 - mean(==), long-double mean) from signatures, two devices
+    rng = np.random.default_rng(3)
+    sig = rng.integers(0, 6, size=(700, 37)).astype(np.uint32)
+    want = port.mh_distance_matrix(sig)
+    got = np.zeros((700, 700), dtype=np.float64, order="F")
+    _lib.check(_lib.lib().dyna_mh_match_matrix(_lib.ptr(sig, __import__("ctypes").c_uint32), 700, 37, _lib.MH_DISTANCE,
+                                              _lib.ptr(got, __import__("ctypes").c_double), 2))
+    eq = (sig[:, None, :] == sig[None, :, :]).sum(axis=2)
+    ref = 1.0 - (eq.astype(np.longdouble) / np.longdouble(37)).astype(np.float64)
+    np.fill_diagonal(ref, 0.0)
+    assert got.tobytes(order="F") == np.asfortranarray(ref).tobytes(order="F")
+    assert got.tobytes(order="F") == np.asfortranarray(want).tobytes(order="F")
 
 
 def _nccl_worker(rank, world, port_no, q):
@@ -69,7 +95,6 @@ def _nccl_worker(rank, world, port_no, q):
 def test_minhash_two_ranks_sharded_relabelling_over_nccl():
     # one process per GPU: row-block plans, relabelling sharded by code rows and completed by one NCCL all-gather
     _need2()
-    import numpy as np
     import torch.multiprocessing as mp
     import os
     ctx = mp.get_context("spawn")
@@ -84,5 +109,5 @@ def test_minhash_two_ranks_sharded_relabelling_over_nccl():
         assert p.exitcode == 0
     assert parts[0][1] and parts[1][1]  # the exchange path was taken
     seqs = synth.peptides_clustered(5000, children=20)
-    want = da.mh_match_counts(da.mh_signatures(seqs, 4, da.hashfamily_seeds(42, 100)))
+    want = port.mh_match_counts(port.mh_signatures(seqs, 4, port.hashfamily_seeds(42, 100)))  # the oracle, not a GPU run
     assert (np.concatenate([parts[0][2], parts[1][2]]) == want).all()

@@ -107,3 +107,49 @@ def test_code_table_exchange_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [(0, True, 1, (0, 8)), (1, True, 1, (8, 16))]
+
+
+def _checksum_worker(rank, world, port_no, q, shift):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import dynaalign_b200 as da
+    from oracle import port
+
+    rng = np.random.default_rng(11)
+    al = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
+    seqs = [al[rng.integers(0, 20, size=int(rng.integers(1, 40)))].tobytes().decode() for _ in range(53)]
+    n = len(seqs)
+    b = da.partition_rows(n, world, weights=[len(s) for s in seqs], include_diagonal=True).tolist()
+    if shift and rank == 1:
+        b[1] += shift  # a deliberate off-by-one in the partition: rank 1 starts one row late
+    rb, re_ = int(b[rank]), int(b[rank + 1])
+    mt, ln = port.nw_pair_stats(seqs, row_begin=rb, row_end=re_)
+    first = rb * n - rb * (rb - 1) // 2
+    mine = (da.checksum(mt, first), da.checksum(ln, first))
+    # bench.py's parity step: gather every rank's pair of sums over the gloo group, add mod 2^64
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    total = tuple(sum(x[k] for x in out) & ((1 << 64) - 1) for k in range(2))
+    if rank == 0:
+        wm, wl = port.nw_pair_stats(seqs)
+        q.put(total == (da.checksum(wm), da.checksum(wl)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shift,expect", [(0, True), (1, False)])
+def test_slab_checksums_add_up_only_for_an_exact_partition(shift, expect):
+    # the multi-GPU parity check of bench.py on CPU: position-weighted checksums of the ranks' slabs sum to the
+    # single-process value, and an off-by-one row in the partition turns the check red
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 30100 + (os.getpid() % 300) + shift
+    procs = [ctx.Process(target=_checksum_worker, args=(r, 2, port_no, q, shift)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got is expect
