@@ -398,7 +398,8 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
   outF = F;
 }
 
-// VAR 3: ONE table.  Per residue class and lane a record of RW score-profile words followed by R increment words,
+// VAR 3: ONE table.  Per residue class and lane a record of RW score-profile words (four int8 scores each) followed
+// by R increment words,
 // padded to a stride of 4*odd words, read only with 128-bit loads (conflict-free: the 8 lanes of a quarter-warp
 // wavefront hit 8 distinct 16-byte bank groups whatever class each lane reads, because the class stride is a multiple
 // of 128 bytes).  Against VAR 2 a column costs one address computation per sequence instead of two and
@@ -406,15 +407,16 @@ __device__ __forceinline__ void strip_column2(const uint32_t (&Ho)[R], uint32_t 
 // VAR 2 (9th increment row, 5th profile word) paying 4 and 2 wavefronts each at strides 12 and 6.
 template <int R>
 struct Rec {
-  static constexpr int RW = Strip<R>::RW;
+  static constexpr int RW = (R + 3) / 4;       // profile words: FOUR int8 scores per word (the equality flag of the
+                                               // 16-bit entries is not needed here -- the increments carry it)
   static constexpr int kWords = RW + R;
   static constexpr int NQ = (kWords + 3) / 4;  // 128-bit loads per record
   static constexpr int kStride = (NQ | 1) * 4; // words per lane record: a multiple of 4, an odd multiple
-  // first strip row that uses a word of quad q (profile word w serves rows 2w and 2w+1; increment word RW+k row k)
+  // first strip row that uses a word of quad q (profile word w serves rows 4w .. 4w+3; increment word RW+k row k)
   __host__ __device__ static constexpr int first_needed(int q) {
     int best = R;
     for (int i = 4 * q; i < 4 * q + 4 && i < kWords; ++i) {
-      const int row = i < RW ? 2 * i : i - RW;
+      const int row = i < RW ? 4 * i : i - RW;
       if (row < best) best = row;
     }
     return best;
@@ -431,14 +433,11 @@ __device__ __forceinline__ void build_records(uint32_t* rec, const uint8_t* __re
     const int rem = idx - cls * (LANES * RC::kStride);
     const int ln = rem / RC::kStride, w = rem - ln * RC::kStride;
     uint32_t v = 0u;
-    if (w < RC::RW) {  // two 16-bit profile entries: low byte = int8 score (+ bias), high byte = residues equal
+    if (w < RC::RW) {  // four int8 scores (+ bias): rows 4w .. 4w+3 of the lane's strip
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int k = 2 * w + h, r = row0 + ln * R + k;
-        if (k < R && r < m && cls < 24) {
-          const int ar = a[r];
-          v |= ((uint32_t)(uint8_t)(sub[ar * 24 + cls] + bias) | (ar == cls ? 0x100u : 0u)) << (16 * h);
-        }
+      for (int h = 0; h < 4; ++h) {
+        const int k = 4 * w + h, r = row0 + ln * R + k;
+        if (k < R && r < m && cls < 24) v |= (uint32_t)(uint8_t)(sub[a[r] * 24 + cls] + bias) << (8 * h);
       }
     } else if (w < RC::kWords) {  // 1 | (row residue == class) << 16; padding rows and class 24 count steps only
       const int k = w - RC::RW, r = row0 + ln * R + k;
@@ -466,8 +465,10 @@ __device__ __forceinline__ void strip_column3(const uint32_t (&Ho)[R], uint32_t 
         wb[4 * q + 0] = vb.x; wb[4 * q + 1] = vb.y; wb[4 * q + 2] = vb.z; wb[4 * q + 3] = vb.w;
       }
     }
-    const uint32_t wA = wa[k >> 1], wB = wb[k >> 1];
-    const uint32_t sP = (k & 1) ? prmt<0xE6A2>(wA, wB) : prmt<0xC480>(wA, wB);  // [sext16(sA) | sext16(sB) << 16]
+    const uint32_t wA = wa[k >> 2], wB = wb[k >> 2];
+    // [sext16(sA) | sext16(sB) << 16] from byte k&3 of both words (selector bit 3 replicates the sign)
+    const uint32_t sP = (k & 3) == 0 ? prmt<0xC480>(wA, wB) : (k & 3) == 1 ? prmt<0xD591>(wA, wB)
+                      : (k & 3) == 2 ? prmt<0xE6A2>(wA, wB) : prmt<0xF7B3>(wA, wB);
     const uint32_t incA = wa[RC::RW + k], incB = wb[RC::RW + k];
     const uint32_t E = El[k];
     const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
@@ -511,8 +512,8 @@ struct Warp2Smem {
   // VAR 2 reads it with 64-bit loads (stride == 2 mod 4 words: conflict-free for the 16 lanes of a wavefront).
   static constexpr bool kProf64 = false;  // measured on the SASS: the register pairs of 64-bit loads cost more moves than the loads save (R = 11: 422 vs 394 instructions per two steps)
   static constexpr int kProfStride = kProf64 ? Strip<R>::RWS64 : Strip<R>::RWS;
-  static constexpr int kProfBytes = 25 * 32 * kProfStride * 4;
-  static constexpr int kIncBytes = VAR == 2 ? 25 * 32 * kIncStride * 4 : 0;
+  static constexpr int kProfBytes = VAR == 3 ? 0 : 25 * 32 * kProfStride * 4;
+  static constexpr int kIncBytes = VAR == 2 ? 25 * 32 * kIncStride * 4 : (VAR == 3 ? 25 * 32 * Rec<R>::kStride * 4 : 0);
   static constexpr int kStageBytes = (THREADS / 32) * 2 * (STAGE + 8);
   static constexpr int kIncOff = 0;                                  // 16-byte aligned first
   static constexpr int kProfOff = kIncOff + kIncBytes;
@@ -531,10 +532,10 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   uint32_t* prof;        // score profile, class 24 = padding residue (all-zero entries)
   uint32_t* incT;        // VAR 2: [class][lane][kIncStride] stat increments
   uint8_t* stage_base;   // per-warp staged column sequences
-  if constexpr (VAR == 2) {
+  if constexpr (VAR == 2 || VAR == 3) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     prof = reinterpret_cast<uint32_t*>(smem_dyn + L::kProfOff);
-    incT = reinterpret_cast<uint32_t*>(smem_dyn + L::kIncOff);
+    incT = reinterpret_cast<uint32_t*>(smem_dyn + L::kIncOff);  // VAR 3: the record table (profile words + increments)
     stage_base = smem_dyn + L::kStageOff;
   } else {
     __shared__ uint32_t prof_s[25 * 32 * L::kProfStride];
@@ -570,8 +571,12 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int m = d.off[row + 1] - d.off[row];
     __syncthreads();
     for (int q = tid; q < un.j_count; q += THREADS) col_len[q] = d.off[un.j_begin + q + 1] - d.off[un.j_begin + q];
-    build_profile<R, 32, L::kProfStride>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
-    for (int idx = tid; idx < 32 * L::kProfStride; idx += THREADS) prof[24 * 32 * L::kProfStride + idx] = 0u;
+    if constexpr (VAR == 3) {
+      build_records<R, 32>(incT, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
+    } else {
+      build_profile<R, 32, L::kProfStride>(prof, d.codes + d.off[row], m, 0, d.sub, 2 * ge, tid, THREADS);
+      for (int idx = tid; idx < 32 * L::kProfStride; idx += THREADS) prof[24 * 32 * L::kProfStride + idx] = 0u;
+    }
     if (VAR == 2) {  // increment table: 1 | (row residue == class) << 16; padding rows and class 24 count steps only
       const uint8_t* __restrict__ a = d.codes + d.off[row];
       for (int idx = tid; idx < 25 * 32 * L::kIncStride; idx += THREADS) {
@@ -599,7 +604,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const bool rot = (lm < 31);  // lane 31 idle: it can hold the border row for lane 0
     const int npairs2 = (un.j_count + 1) >> 1;
     const uint32_t plane_sh = (uint32_t)__cvta_generic_to_shared(prof + lane * L::kProfStride);
-    const uint32_t ilane_sh = (uint32_t)__cvta_generic_to_shared(incT + lane * L::kIncStride);
+    const uint32_t ilane_sh = (uint32_t)__cvta_generic_to_shared(incT + lane * (VAR == 3 ? Rec<R>::kStride : L::kIncStride));
 
     for (int pp = warp; pp < npairs2; pp += nwarps) {
       const bool hasB = (2 * pp + 1 < un.j_count);
@@ -668,38 +673,48 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
           }
           if ((unsigned)jc < n_act) {
             const uint32_t cA = lds_u8(sA_sh + (uint32_t)jc), cB = lds_u8(sB_sh + (uint32_t)jc);
-            uint32_t pwA[S::RW], pwB[S::RW];
-            const uint32_t pa = plane_sh + cA * (32u * L::kProfStride * 4u);
-            const uint32_t pb = plane_sh + cB * (32u * L::kProfStride * 4u);
-            const uint32_t ia = ilane_sh + cA * (32u * L::kIncStride * 4u);
-            const uint32_t ib = ilane_sh + cB * (32u * L::kIncStride * 4u);
-            if constexpr (L::kProf64) {
-#pragma unroll
-              for (int w = 0; w < S::RW; w += 2) {  // an odd RW reads one padding word of the lane's stride
-                const uint2 va = lds_v2(pa + 4u * (unsigned)w), vb = lds_v2(pb + 4u * (unsigned)w);
-                pwA[w] = va.x;
-                pwB[w] = vb.x;
-                if (w + 1 < S::RW) {
-                  pwA[w + 1] = va.y;
-                  pwB[w + 1] = vb.y;
+            if constexpr (VAR == 3) {
+              const uint32_t ra = ilane_sh + cA * (32u * Rec<R>::kStride * 4u);
+              const uint32_t rb = ilane_sh + cB * (32u * Rec<R>::kStride * 4u);
+              if (ph == 0) {
+                strip_column3<R>(H0, H1, El, SA0, SA1, SB0, SB1, ra, rb, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              } else {
+                strip_column3<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, rb, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              }
+            } else {
+              uint32_t pwA[S::RW], pwB[S::RW];
+              const uint32_t pa = plane_sh + cA * (32u * L::kProfStride * 4u);
+              const uint32_t pb = plane_sh + cB * (32u * L::kProfStride * 4u);
+              const uint32_t ia = ilane_sh + cA * (32u * L::kIncStride * 4u);
+              const uint32_t ib = ilane_sh + cB * (32u * L::kIncStride * 4u);
+              if constexpr (L::kProf64) {
+  #pragma unroll
+                for (int w = 0; w < S::RW; w += 2) {  // an odd RW reads one padding word of the lane's stride
+                  const uint2 va = lds_v2(pa + 4u * (unsigned)w), vb = lds_v2(pb + 4u * (unsigned)w);
+                  pwA[w] = va.x;
+                  pwB[w] = vb.x;
+                  if (w + 1 < S::RW) {
+                    pwA[w + 1] = va.y;
+                    pwB[w + 1] = vb.y;
+                  }
+                }
+              } else {
+  #pragma unroll
+                for (int w = 0; w < S::RW; ++w) {
+                  pwA[w] = lds_u32(pa + 4u * (unsigned)w);
+                  pwB[w] = lds_u32(pb + 4u * (unsigned)w);
                 }
               }
-            } else {
-#pragma unroll
-              for (int w = 0; w < S::RW; ++w) {
-                pwA[w] = lds_u32(pa + 4u * (unsigned)w);
-                pwB[w] = lds_u32(pb + 4u * (unsigned)w);
+              if constexpr (INPLACE) {
+                strip_column2<R, VAR>(H0, H0, El, SA0, SA0, SB0, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                      ngo2, c, outF, ia, ib);
+              } else if (ph == 0) {
+                strip_column2<R, VAR>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                      ngo2, c, outF, ia, ib);
+              } else {
+                strip_column2<R, VAR>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
+                                      ngo2, c, outF, ia, ib);
               }
-            }
-            if constexpr (INPLACE) {
-              strip_column2<R, VAR>(H0, H0, El, SA0, SA0, SB0, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
-                                    ngo2, c, outF, ia, ib);
-            } else if (ph == 0) {
-              strip_column2<R, VAR>(H0, H1, El, SA0, SA1, SB0, SB1, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
-                                    ngo2, c, outF, ia, ib);
-            } else {
-              strip_column2<R, VAR>(H1, H0, El, SA1, SA0, SB1, SB0, pwA, pwB, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB,
-                                    ngo2, c, outF, ia, ib);
             }
             prevUpH = rH;
             prevUpSA = rSA;
@@ -1431,7 +1446,7 @@ int launch_warp_R(bool slant, const NwDeviceData& d, const NwUnit* d_units, int 
 template <int R, int VAR, bool INPLACE, int THREADS>
 int launch_warp2_inst(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   using L = Warp2Smem<R, VAR, THREADS>;
-  if constexpr (VAR == 2) {
+  if constexpr (VAR == 2 || VAR == 3) {
     DYNA_CUDA(cudaFuncSetAttribute(nw_warp2_kernel<R, VAR, INPLACE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     nw_warp2_kernel<R, VAR, INPLACE, THREADS><<<num_units, THREADS, L::kTotal, st>>>(d, d_units, num_units);
   } else {
@@ -1444,15 +1459,18 @@ int launch_warp2_inst(const NwDeviceData& d, const NwUnit* d_units, int num_unit
 template <int R>
 int launch_warp2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   // measured on B200 (TCUPS, config 5 / config 2):
-  //   strips R <= 12: ping-pong register sets, 8-warp CTAs, increments from the shared-memory table (VAR 2): 2.94
+  //   strips R <= 12: ping-pong register sets, 8-warp CTAs, record table (VAR 3: int8 scores and increments in one record
+  //                   per lane and class, 128-bit loads only): 3.38 against 3.26 for VAR 2 on the same box (round 2)
+  //   history of VAR 2 (increments from their own shared-memory table): 2.94
   //                   (VAR 1, increments by PRMT: 2.72 on the same box; one register set: 2.58; with the final step
   //                   loop: table for all rows 3.17, for the first 8 rows 3.12, first 4 rows 3.08, PRMT only 3.00)
   //   strips R >= 13: one register set, 4-warp CTAs, increments by PRMT (VAR 1): 2.60 (VAR 2: 2.48; ping-pong: 2.27;
   //                   VAR 2 with one register set in 8-warp CTAs at 128 registers, 16 warps/SM, R <= 18: 2.56)
   if constexpr (R >= 13) return launch_warp2_inst<R, 1, true, 128>(d, d_units, num_units, st);
   else {
-    const int var = getenv("DYNA_NW2_VARIANT") ? atoi(getenv("DYNA_NW2_VARIANT")) : 2;
+    const int var = getenv("DYNA_NW2_VARIANT") ? atoi(getenv("DYNA_NW2_VARIANT")) : 3;
     if (var == 1) return launch_warp2_inst<R, 1, false, kWarpThreads>(d, d_units, num_units, st);
+    if (var == 3) return launch_warp2_inst<R, 3, false, kWarpThreads>(d, d_units, num_units, st);
     return launch_warp2_inst<R, 2, false, kWarpThreads>(d, d_units, num_units, st);
   }
 }
