@@ -697,7 +697,8 @@ extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
 // =====================================================================================================
 struct NwClass {
   int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit,
-             // 6 two-pairs-per-warp 16-bit, several passes, 7 two-pairs-per-warp-pair 16-bit (cooperating warps)
+             // 6 two-pairs-per-warp 16-bit, several passes, 7 two-pairs-per-warp-pair 16-bit (cooperating warps),
+             // 8 two ROWS per warp 16-bit (units[].row and row+1 against the same column sequences), 9 its cooperative form
   int R;
   int64_t work = 0;  // DP cells of the class (launch order: largest first)
   std::vector<NwUnit> units;
@@ -807,6 +808,17 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   if (const char* e = getenv("DYNA_NW_CO")) use_co = atoi(e) != 0;
   // columns per unit of the packed single-pass kernel: wide units amortise the per-unit table build (+0.9 % at
   // BASELINE config 5), but a small input needs the finer grain to fill 296 CTA slots (config 2: 2975 vs 2880 GCUPS)
+  // rows of 33..384 residues are taken two at a time (rows i, i+1 against the same columns: nw_rows2_kernel);
+  // DYNA_NW_ROWS2=0 restores one row against two column sequences (nw_warp2_kernel) for A/B measurements
+  // (its units are two rows x 256 columns on a whole SM: only for inputs large enough to fill the GPU with them)
+  bool use_rows2 = p->pairs >= (int64_t)kNwWarp2UnitColsMax * kNwMultiPassGrid * 32;
+  if (const char* e = getenv("DYNA_NW_ROWS2")) use_rows2 = atoi(e) != 0;
+  // the cooperative form of the same (row pairs of 385..576 residues).  Units of 128 columns also on small inputs
+  // (BASELINE config 2: 3337 GCUPS against 3291 at 64 and 3207 at 32 columns)
+  bool use_rows2co = use_co;
+  if (const char* e = getenv("DYNA_NW_ROWS2CO")) use_rows2co = use_rows2co && atoi(e) != 0;
+  int rows2co_cols = kNwCoUnitCols;
+  if (const char* e = getenv("DYNA_NW_ROWS2CO_COLS")) rows2co_cols = std::min(kNwCoUnitCols, std::max(1, atoi(e)));
   int warp2_cols = p->pairs >= (int64_t)kNwWarp2UnitColsMax * kNwMultiPassGrid * 32 ? kNwWarp2UnitColsMax : kNwWarp2UnitCols;
   if (const char* e = getenv("DYNA_NW_UNITCOLS")) warp2_cols = std::min(kNwWarp2UnitColsMax, std::max(2, atoi(e) & ~1));
 
@@ -867,6 +879,39 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   for (int64_t i = 0; i < n; ++i) len_prefix[(size_t)i + 1] = len_prefix[(size_t)i] + (offsets[i + 1] - offsets[i]);
   for (int64_t i = row_begin; i < row_end; ++i) {
     const int m = (int)(offsets[i + 1] - offsets[i]);
+    if ((use_rows2 || use_rows2co) && !force_warp2 && i + 1 < row_end) {
+      // two-rows kernel: both rows in the single-pass packed range, similar length (the strip layout follows the longer
+      // one), and EVERY column sequence they meet within the 16-bit value range and the staging buffer
+      const int m2 = (int)(offsets[i + 2] - offsets[i + 1]);
+      const int mx = std::max(m, m2), mn = std::min(m, m2);
+      if (use_rows2co && mn >= kNwCoMinRows && mx <= kNwRows2CoMaxRows && nw_co_R(mx) >= 7 && (mn - 1) / (32 * nw_co_R(mx)) == 1) {
+        // cooperative form: both rows reach into the second warp's block of 32*R rows
+        const int64_t nmax = range_max(i, n);
+        if (fits16u(mx, nmax) && nmax <= kNwWarp2MaxCols) {
+          NwClass* cls = get_class(9, nw_co_R(mx));
+          for (int64_t j = i; j < n; j += rows2co_cols) {
+            const int64_t cnt = std::min<int64_t>(rows2co_cols, n - j);
+            cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
+            cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
+          }
+          ++i;
+          continue;
+        }
+      }
+      if (use_rows2 && mn > kNwThreadMaxRows && mx <= 32 * 12 && 4 * mn >= 3 * mx) {
+        const int64_t nmax = range_max(i, n);
+        if (fits16u(mx, nmax) && nmax <= kNwWarp2MaxCols) {
+          NwClass* cls = get_class(8, nw_warp_R(mx));
+          for (int64_t j = i; j < n; j += kNwRows2UnitCols) {
+            const int64_t cnt = std::min<int64_t>(kNwRows2UnitCols, n - j);
+            cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
+            cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
+          }
+          ++i;  // row i+1 is covered
+          continue;
+        }
+      }
+    }
     int64_t j = i;
     while (j < n) {
       int kind, R, step;
@@ -953,6 +998,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
   d.gap_open = p->gap_open;
   d.gap_ext = p->gap_ext;
   d.one = 1u;
+  d.zero = 0u;
   p->launches = 0;
   p->last_stream = st;
   const bool fork = p->side[0] != nullptr;
@@ -990,6 +1036,8 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       case 5: DYNA_TRY(launch_nw_thread2(c->R, d, c->d_units.p, nu, cs)); break;
       case 6: DYNA_TRY(launch_nw_warp2mp(c->R, d, c->d_units.p, nu, p->scratch2.p, cs)); break;
       case 7: DYNA_TRY(launch_nw_warp2co(c->R, d, c->d_units.p, nu, cs)); break;
+      case 8: DYNA_TRY(launch_nw_rows2(c->R, d, c->d_units.p, nu, cs)); break;
+      case 9: DYNA_TRY(launch_nw_rows2co(c->R, d, c->d_units.p, nu, cs)); break;
       default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, cs)); break;
     }
     ++p->launches;

@@ -759,6 +759,228 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5x2 "two rows": the two 16-bit halves of every score register belong to two ROW sequences -- rows i and i+1 of the
+// triangle -- aligned against the SAME column sequence, instead of one row sequence against two column sequences.
+// Both halves then see the same residue class c in every column, so
+//   * the packed score operand [s(a2_k, c) : s(a1_k, c)] is ONE precomputed table word: the PRMT that merged the scores
+//     of two classes (an ALU-pipe instruction per row, the pipe this kernel loads most) is gone;
+//   * there is one staged column sequence, one residue load, one table address and one record stream per step;
+//   * the shorter-column padding (class 24, result capture at the shorter sequence's last column, pairing the columns
+//     by length) disappears: both alignments end in the same column, only in different rows.
+// Record per (class, lane): for each of the R strip rows three words -- packed scores, increment of pair 1 (1 | a1_k == c
+// << 16), increment of pair 2 -- read with 128-bit loads a few rows ahead of their use (stride 4*odd words: conflict-free
+// whatever class each lane reads).  3R words per lane and class is ~110 KB for R = 11, so a CTA owns a whole SM: 16
+// warps, one unit = the two rows against up to 256 column sequences (16 per warp).
+// The two rows have different lengths m1, m2: the strip layout follows the longer one, the rows the shorter one lacks
+// are zero-score padding below its last row and are never read back (each result is taken from its own last row).
+// Column j = i (the first row against itself) has no counterpart for row i+1; that half is computed and dropped.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRows2Threads = 512;
+
+template <int R>
+struct Rec2 {
+  static constexpr int kWords = 3 * R;
+  static constexpr int NQ = (kWords + 3) / 4;   // 128-bit loads per record
+  static constexpr int kStride = (NQ | 1) * 4;  // words per lane record: a multiple of 4, an odd multiple
+  static constexpr int kTableBytes = 24 * 32 * kStride * 4;
+  static constexpr int kStageBytes = (kRows2Threads / 32) * (kNwStageCols + 8);
+  static constexpr int kTotal = kTableBytes + kStageBytes;
+  __host__ __device__ static constexpr int first_needed(int q) { return (4 * q) / 3; }  // row of the quad's first word
+  __host__ __device__ static constexpr int load_row(int q) { return first_needed(q) >= 2 ? first_needed(q) - 2 : 0; }
+};
+
+template <int R>
+__device__ __forceinline__ void build_records2(uint32_t* rec, const uint8_t* __restrict__ a1, int m1,
+                                               const uint8_t* __restrict__ a2, int m2, const int8_t* __restrict__ sub, int bias,
+                                               int tid, int nthreads) {
+  using RC = Rec2<R>;
+  for (int idx = tid; idx < 24 * 32 * RC::kStride; idx += nthreads) {
+    const int cls = idx / (32 * RC::kStride);
+    const int rem = idx - cls * (32 * RC::kStride);
+    const int ln = rem / RC::kStride, w = rem - ln * RC::kStride;
+    uint32_t v = 0u;
+    if (w < RC::kWords) {
+      const int k = w / 3, t = w - 3 * k, r = ln * R + k;
+      if (t == 0) {  // packed scores, sign-extended to 16 bits each; rows beyond a sequence's end score 0
+        const int s1 = r < m1 ? (int)(int8_t)(sub[a1[r] * 24 + cls] + bias) : 0;
+        const int s2 = r < m2 ? (int)(int8_t)(sub[a2[r] * 24 + cls] + bias) : 0;
+        v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
+      } else if (t == 1) {
+        v = 1u | ((r < m1 && a1[r] == cls) ? 0x10000u : 0u);
+      } else {
+        v = 1u | ((r < m2 && a2[r] == cls) ? 0x10000u : 0u);
+      }
+    }
+    rec[idx] = v;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
+                                              const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
+                                              uint32_t (&SBn)[R], uint32_t rec_sh, uint32_t diagH, uint32_t dSA, uint32_t dSB,
+                                              uint32_t F, uint32_t upSA, uint32_t upSB, uint32_t ngo2, const Stat2Consts& c,
+                                              uint32_t& outF) {
+  using RC = Rec2<R>;
+  uint32_t w[RC::NQ * 4];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+#pragma unroll
+    for (int q = 0; q < RC::NQ; ++q) {
+      if (RC::load_row(q) == k) {
+        const uint4 v = lds_v4(rec_sh + 16u * (unsigned)q);
+        w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+    }
+    const uint32_t sP = w[3 * k], incA = w[3 * k + 1], incB = w[3 * k + 2];
+    const uint32_t E = El[k];
+    const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    bool puB, puA, pdB, pdA;
+    const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);   // pred_hi -> pair 2 (row i+1), pred_lo -> pair 1 (row i)
+    const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    const uint32_t SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
+    diagH = Ho[k];
+    dSA = SAo[k];
+    dSB = SBo[k];
+    Hn[k] = H;
+    SAn[k] = SA;
+    SBn[k] = SB;
+    El[k] = __viaddmax_s16x2(H, ngo2, E);
+    F = __viaddmax_s16x2(H, ngo2, F);
+    upSA = SA;
+    upSB = SB;
+  }
+  outF = F;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kRows2Threads, 1)
+nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  using RC = Rec2<R>;
+  constexpr int nwarps = kRows2Threads / 32;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  uint32_t* rec = reinterpret_cast<uint32_t*>(smem_dyn);
+  uint8_t* stage_base = smem_dyn + RC::kTableBytes;
+  __shared__ uint32_t res_m1[kNwRows2UnitCols], res_l1[kNwRows2UnitCols], res_m2[kNwRows2UnitCols], res_l2[kNwRows2UnitCols];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.zero;
+  const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // register operand (see nw_thread2_kernel)
+  const uint32_t bord2 = pack16(ge - go);               // slanted border: -go + ge for every k >= 1
+  const unsigned full = 0xFFFFFFFFu;
+  const int src_lane = (lane + 31) & 31;  // rotating "shuffle up": lane 0 reads lane 31
+  uint8_t* sC = stage_base + warp * (kNwStageCols + 8);
+  const uint32_t sC_sh = (uint32_t)__cvta_generic_to_shared(sC);
+  const uint32_t rlane_sh = (uint32_t)__cvta_generic_to_shared(rec + lane * RC::kStride);
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row, row2 = un.row + 1;
+    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
+    __syncthreads();
+    build_records2<R>(rec, d.codes + d.off[row], m1, d.codes + d.off[row2], m2, d.sub, 2 * ge, tid, kRows2Threads);
+    __syncthreads();
+    const int lmA = (m1 - 1) / R, kmA = (m1 - 1) - lmA * R;
+    const int lmB = (m2 - 1) / R, kmB = (m2 - 1) - lmB * R;
+    const int lm = max(lmA, lmB);
+    const int r0 = lane * R;
+    const bool rot = (lm < 31);  // lane 31 idle: it holds the border row for lane 0
+
+    for (int pp = warp; pp < un.j_count; pp += nwarps) {
+      const int j = un.j_begin + pp;
+      const int n = d.off[j + 1] - d.off[j];
+      {
+        const uint8_t* __restrict__ b = d.codes + d.off[j];
+        __syncwarp();
+        for (int q = lane; q < n; q += 32) sC[q] = b[q];
+        __syncwarp();
+      }
+      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        H0[k] = H1[k] = bord2;
+        El[k] = sent2;
+        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+      }
+      uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
+      uint32_t prevUpSA = 0u, prevUpSB = 0u;
+      uint32_t outF = sent2;
+      const unsigned n_act = (lane <= lm) ? (unsigned)n : 0u;
+      const int T = n + lm;
+      auto run_steps = [&](auto rot_c) {
+        constexpr bool ROT = decltype(rot_c)::value;
+        for (int t0 = 0; t0 < T; t0 += 2) {
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int jc = t0 + ph - lane;
+            uint32_t rH = __shfl_sync(full, ph == 1 ? H1[R - 1] : H0[R - 1], src_lane);
+            uint32_t rF = __shfl_sync(full, outF, src_lane);
+            uint32_t rSA = __shfl_sync(full, ph == 1 ? SA1[R - 1] : SA0[R - 1], src_lane);
+            uint32_t rSB = __shfl_sync(full, ph == 1 ? SB1[R - 1] : SB0[R - 1], src_lane);
+            if (!ROT) {  // all 32 lanes own rows: lane 0 takes the border row explicitly
+              if (lane == 0) {
+                rH = bord2;
+                rF = sent2;
+                rSA = 0u;
+                rSB = 0u;
+              }
+            }
+            if ((unsigned)jc < n_act) {
+              const uint32_t cc = lds_u8(sC_sh + (uint32_t)jc);
+              const uint32_t ra = rlane_sh + cc * (32u * RC::kStride * 4u);
+              if (ph == 0) {
+                strip_column4<R>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              } else {
+                strip_column4<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              }
+              prevUpH = rH;
+              prevUpSA = rSA;
+              prevUpSB = rSB;
+            }
+          }
+        }
+      };
+      if (rot) run_steps(std::true_type{});
+      else run_steps(std::false_type{});
+      // every lane finished its last column at step lane + n - 1, which wrote register set ((lane + n) & 1)
+      const bool in1 = (((lane + n) & 1) != 0);
+      uint32_t resA = 0u, resB = 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (k == kmA) resA = in1 ? SA1[k] : SA0[k];
+        if (k == kmB) resB = in1 ? SB1[k] : SB0[k];
+      }
+      resA = __shfl_sync(full, resA, lmA);
+      resB = __shfl_sync(full, resB, lmB);
+      if (lane == 0) {  // stat word: matches << 16 | diagonal steps;  length = m + n - diagonal steps
+        res_m1[pp] = resA >> 16;
+        res_l1[pp] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
+        res_m2[pp] = resB >> 16;
+        res_l2[pp] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+      }
+    }
+    __syncthreads();
+    {  // both rows' pairs occupy consecutive slots of the packed triangle; column `row` exists for the first row only
+      const int64_t slot1 = pair_slot(d.n, row, un.j_begin, d.slab_base);
+      const int skip = un.j_begin < row2 ? row2 - un.j_begin : 0;
+      const int64_t slot2 = pair_slot(d.n, row2, un.j_begin + skip, d.slab_base) - skip;
+      for (int q = tid; q < un.j_count; q += kRows2Threads) {
+        d.matches[slot1 + q] = res_m1[q];
+        d.length[slot1 + q] = res_l1[q];
+        if (q >= skip) {
+          d.matches[slot2 + q] = res_m2[q];
+          d.length[slot2 + q] = res_l2[q];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5x2 multi-pass: the packed two-pairs kernel for rows longer than one pass of 32*R rows (R <= 12 keeps the fast
 // ping-pong / increment-table configuration).  The CTA walks the row sequence in passes of 32*R rows; within a pass
 // every warp processes its pair-sets exactly like nw_warp2_kernel, except that
@@ -1255,6 +1477,226 @@ nw_warp2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5x2 cooperative + two rows: the cooperative wavefront of nw_warp2co_kernel (K warps, ring between neighbours) with
+// the operand layout of nw_rows2_kernel (rows i and i+1 in the two 16-bit halves, one column sequence, one record
+// stream, no score PRMT).  3R words per lane and class over 32*K lanes is 172 KB for R <= 9, K = 2 -- what fits next to
+// the rings and the staged sequences -- so it serves row pairs of 385..576 residues: the 566-residue HA sequences of
+// BASELINE config 2.  Rings: one per producer warp, one shared sink for the last warp of every group (its bottom row
+// is never read), one constant border entry.
+// ------------------------------------------------------------------------------------------------
+template <int R, int K>
+struct Rows2CoSmem {
+  static constexpr int kLanes = 32 * K;
+  static constexpr int kWarps = kCoThreads / 32;
+  static constexpr int kGroups = kWarps / K;
+  static constexpr int kStride = Rec2<R>::kStride;
+  static constexpr int kRings = kGroups * (K - 1) + 1;            // producers' rings + the sink
+  static constexpr int kRingBytes = kRings * kCoRing * 16;
+  static constexpr int kTableBytes = 24 * kLanes * kStride * 4;
+  static constexpr int kStageBytes = kWarps * (kNwStageCols + 8);
+  static constexpr int kRingOff = 0;                              // from the first 2048-byte aligned address
+  static constexpr int kTableOff = kRingOff + kRingBytes;
+  static constexpr int kStageOff = kTableOff + kTableBytes;
+  static constexpr int kTotal = kStageOff + kStageBytes + 2048;
+};
+
+template <int R, int K>
+__global__ void __launch_bounds__(kCoThreads, 1)
+nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  using RC = Rec2<R>;
+  using L = Rows2CoSmem<R, K>;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ uint32_t res_m1[kNwCoUnitCols], res_l1[kNwCoUnitCols], res_m2[kNwCoUnitCols], res_l2[kNwCoUnitCols];
+  __shared__ uint32_t prod_cnt[L::kWarps], cons_cnt[L::kWarps];
+  __shared__ __align__(16) uint4 border_entry;
+  const uint32_t dyn_sh = ((uint32_t)__cvta_generic_to_shared(smem_dyn) + 2047u) & ~2047u;
+  unsigned char* dyn = smem_dyn + (dyn_sh - (uint32_t)__cvta_generic_to_shared(smem_dyn));
+  uint32_t* rec = reinterpret_cast<uint32_t*>(dyn + L::kTableOff);
+  uint8_t* stage_base = dyn + L::kStageOff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int group = warp / K, role = warp - group * K;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.zero;
+  const uint32_t sent2 = pack16(kSentinel16) + c.zero;
+  const uint32_t bord2 = pack16(ge - go);
+  const unsigned full = 0xFFFFFFFFu;
+  const int src_lane = (lane + 31) & 31;
+  const bool producer = role < K - 1, consumer = role > 0;
+  uint8_t* sC = stage_base + warp * (kNwStageCols + 8);
+  const uint32_t sC_sh = (uint32_t)__cvta_generic_to_shared(sC);
+  const uint32_t rlane_sh = (uint32_t)__cvta_generic_to_shared(rec + (role * 32 + lane) * L::kStride);
+  // ring this warp writes: its own when another warp of the group consumes it, the shared sink otherwise
+  const uint32_t out_ring_sh = dyn_sh + L::kRingOff + (uint32_t)(producer ? group * (K - 1) + role : L::kRings - 1) * (kCoRing * 16);
+  const uint32_t in_ring_sh = consumer ? dyn_sh + L::kRingOff + (uint32_t)(group * (K - 1) + role - 1) * (kCoRing * 16)
+                                       : (uint32_t)__cvta_generic_to_shared(&border_entry);
+  const uint32_t in_mask16 = consumer ? (uint32_t)(kCoRing * 16 - 16) : 0u;
+  const uint32_t out_mask16 = (uint32_t)(kCoRing * 16 - 16);
+  const uint32_t my_prod_sh = (uint32_t)__cvta_generic_to_shared(&prod_cnt[warp]);
+  const uint32_t my_cons_sh = (uint32_t)__cvta_generic_to_shared(&cons_cnt[warp]);
+  const uint32_t up_prod_sh = (uint32_t)__cvta_generic_to_shared(&prod_cnt[consumer ? warp - 1 : warp]);
+  const uint32_t dn_cons_sh = (uint32_t)__cvta_generic_to_shared(&cons_cnt[producer ? warp + 1 : warp]);
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row, row2 = un.row + 1;
+    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
+    __syncthreads();
+    if (tid < L::kWarps) prod_cnt[tid] = cons_cnt[tid] = 0u;
+    if (tid == 0) border_entry = make_uint4(bord2, sent2, 0u, 0u);
+    {  // records of all 32*K lanes
+      const uint8_t* __restrict__ a1 = d.codes + d.off[row];
+      const uint8_t* __restrict__ a2 = d.codes + d.off[row2];
+      for (int idx = tid; idx < 24 * L::kLanes * L::kStride; idx += kCoThreads) {
+        const int cls = idx / (L::kLanes * L::kStride);
+        const int rem = idx - cls * (L::kLanes * L::kStride);
+        const int ln = rem / L::kStride, w = rem - ln * L::kStride;
+        uint32_t v = 0u;
+        if (w < RC::kWords) {
+          const int k = w / 3, t = w - 3 * k, r = ln * R + k;
+          if (t == 0) {
+            const int s1 = r < m1 ? (int)(int8_t)(d.sub[a1[r] * 24 + cls] + 2 * ge) : 0;
+            const int s2 = r < m2 ? (int)(int8_t)(d.sub[a2[r] * 24 + cls] + 2 * ge) : 0;
+            v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
+          } else if (t == 1) {
+            v = 1u | ((r < m1 && a1[r] == cls) ? 0x10000u : 0u);
+          } else {
+            v = 1u | ((r < m2 && a2[r] == cls) ? 0x10000u : 0u);
+          }
+        }
+        rec[idx] = v;
+      }
+    }
+    __syncthreads();
+    const int LmA = (m1 - 1) / R, kmA = (m1 - 1) - LmA * R;  // last lane (0 .. 32K-1) and strip row of each sequence
+    const int LmB = (m2 - 1) / R, kmB = (m2 - 1) - LmB * R;
+    const int Lm = max(LmA, LmB);
+    const int last_role = Lm >> 5;  // host guarantees last_role == K-1
+    const int lm = (role < last_role) ? 31 : (Lm & 31);
+    const bool ownA = (role == (LmA >> 5)), ownB = (role == (LmB >> 5));
+    const int r0 = (role * 32 + lane) * R;
+    int base_p = 0, base_c = 0;
+    int seen_prod = 0, seen_cons = 0;
+
+    for (int pp = group; pp < un.j_count; pp += L::kGroups) {
+      const int j = un.j_begin + pp;
+      const int n = d.off[j + 1] - d.off[j];
+      {
+        const uint8_t* __restrict__ b = d.codes + d.off[j];
+        __syncwarp();
+        for (int q = lane; q < n; q += 32) sC[q] = b[q];
+        __syncwarp();
+      }
+      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        H0[k] = H1[k] = bord2;
+        El[k] = sent2;
+        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+      }
+      uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
+      uint32_t prevUpSA = 0u, prevUpSB = 0u;
+      uint32_t outF = sent2;
+      const unsigned n_act = (lane <= lm) ? (unsigned)n : 0u;
+      const int T = n + lm + (producer ? 1 : 0);
+      uint32_t out_addr = out_ring_sh | (((uint32_t)(base_p - 32) * 16u) & out_mask16);
+      uint32_t in_addr = in_ring_sh | (((uint32_t)base_c * 16u) & in_mask16);
+      for (int tc = 0; tc < T; tc += kCoChunk) {
+        const int tend = min(tc + kCoChunk, T);
+        if (consumer) {
+          const int need = base_c + min(tend, n);
+          while (seen_prod < need) seen_prod = (int)ld_acquire_shared(up_prod_sh);
+        }
+        if (producer) {
+          const int top = base_p + tend + 1 - 32;
+          while (top - seen_cons > kCoRing) seen_cons = (int)ld_acquire_shared(dn_cons_sh);
+        }
+        if (lane == 0) {
+          if (producer) st_release_shared(my_prod_sh, (uint32_t)(base_p + max(tc - 32, 0)));
+          if (consumer) st_release_shared(my_cons_sh, (uint32_t)(base_c + min(tc, n)));
+        }
+        for (int t0 = tc; t0 < tend; t0 += 2) {
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int jc = t0 + ph - lane;
+            uint32_t rH = __shfl_sync(full, ph == 1 ? H1[R - 1] : H0[R - 1], src_lane);
+            uint32_t rF = __shfl_sync(full, outF, src_lane);
+            uint32_t rSA = __shfl_sync(full, ph == 1 ? SA1[R - 1] : SA0[R - 1], src_lane);
+            uint32_t rSB = __shfl_sync(full, ph == 1 ? SB1[R - 1] : SB0[R - 1], src_lane);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.eq.u32 p, %6, 0;\n\t"
+                "@p st.shared.v4.u32 [%4], {%0, %1, %2, %3};\n\t"
+                "@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n\t}"
+                : "+r"(rH), "+r"(rF), "+r"(rSA), "+r"(rSB)
+                : "r"(out_addr), "r"(in_addr), "r"(lane)
+                : "memory");
+            out_addr = out_ring_sh | ((out_addr + 16u) & out_mask16);
+            in_addr = in_ring_sh | ((in_addr + 16u) & in_mask16);
+            if ((unsigned)jc < n_act) {
+              const uint32_t cc = lds_u8(sC_sh + (uint32_t)jc);
+              const uint32_t ra = rlane_sh + cc * (uint32_t)(L::kLanes * L::kStride * 4);
+              if (ph == 0) {
+                strip_column4<R>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              } else {
+                strip_column4<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              }
+              prevUpH = rH;
+              prevUpSA = rSA;
+              prevUpSB = rSB;
+            }
+          }
+        }
+      }
+      base_p += n + kCoGap;
+      base_c += n + kCoGap;
+      __syncwarp();
+      if (lane == 0) {
+        if (producer) st_release_shared(my_prod_sh, (uint32_t)base_p);
+        if (consumer) st_release_shared(my_cons_sh, (uint32_t)base_c);
+      }
+      if (ownA || ownB) {
+        const bool in1 = (((lane + n) & 1) != 0);  // the set this lane's last column (step lane + n - 1) wrote
+        uint32_t resA = 0u, resB = 0u;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          if (k == kmA) resA = in1 ? SA1[k] : SA0[k];
+          if (k == kmB) resB = in1 ? SB1[k] : SB0[k];
+        }
+        resA = __shfl_sync(full, resA, LmA & 31);
+        resB = __shfl_sync(full, resB, LmB & 31);
+        if (lane == 0) {
+          if (ownA) {
+            res_m1[pp] = resA >> 16;
+            res_l1[pp] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
+          }
+          if (ownB) {
+            res_m2[pp] = resB >> 16;
+            res_l2[pp] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int64_t slot1 = pair_slot(d.n, row, un.j_begin, d.slab_base);
+      const int skip = un.j_begin < row2 ? row2 - un.j_begin : 0;
+      const int64_t slot2 = pair_slot(d.n, row2, un.j_begin + skip, d.slab_base) - skip;
+      for (int q = tid; q < un.j_count; q += kCoThreads) {
+        d.matches[slot1 + q] = res_m1[q];
+        d.length[slot1 + q] = res_l1[q];
+        if (q >= skip) {
+          d.matches[slot2 + q] = res_m2[q];
+          d.length[slot2 + q] = res_l2[q];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: one thread per pair (rows <= R <= 32)
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreadThreads = 128;
@@ -1581,6 +2023,51 @@ int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 #undef DYNA_CASE
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw cooperative warp2 kernel: unsupported strip height %d", R);
+  }
+}
+
+template <int R>
+int launch_rows2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  using RC = Rec2<R>;
+  DYNA_CUDA(cudaFuncSetAttribute(nw_rows2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, RC::kTotal));
+  nw_rows2_kernel<R><<<num_units, kRows2Threads, RC::kTotal, st>>>(d, d_units, num_units);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_rows2_R<RR>(d, d_units, num_units, st);
+    DYNA_CASE(2) DYNA_CASE(3) DYNA_CASE(4) DYNA_CASE(5) DYNA_CASE(6) DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9)
+    DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw two-rows kernel: unsupported strip height %d", R);
+  }
+}
+
+template <int R>
+int launch_rows2co_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  using L = Rows2CoSmem<R, 2>;
+  DYNA_CUDA(cudaFuncSetAttribute(nw_rows2co_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  nw_rows2co_kernel<R, 2><<<num_units, kCoThreads, L::kTotal, st>>>(d, d_units, num_units);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_rows2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_rows2co_R<RR>(d, d_units, num_units, st);
+    DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw cooperative two-rows kernel: unsupported strip height %d", R);
   }
 }
 

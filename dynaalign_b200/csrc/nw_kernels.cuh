@@ -22,6 +22,7 @@ struct NwDeviceData {
   uint32_t* length;
   int gap_open, gap_ext;
   uint32_t one;          // always 1; passed as data so the compiler keeps it in a register (see strip_column)
+  uint32_t zero;         // always 0; an opaque addend that lives in a uniform register / constant operand (see stat_select)
 };
 
 constexpr int kNwThreadMaxRows = 32;  // rows handled by the thread-per-pair kernel
@@ -59,6 +60,14 @@ constexpr int kNwCoMinRows = 32 * 12 + 1;
 constexpr int kNwCoMaxRows = 64 * 12;
 inline int nw_co_R(int m) { return (m + 63) / 64; }
 int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
+// two-rows packed kernel: rows i and i+1 (33..384 residues each, strips R <= 12) against the same column sequences;
+// a unit is the row pair against up to kNwRows2UnitCols column sequences (units[].row is the first row)
+constexpr int kNwRows2UnitCols = 256;
+int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
+// cooperative two-rows kernel: row pairs of 385..576 residues (R = ceil(max/64) <= 9: what its tables allow in 227 KB);
+// units of up to kNwCoUnitCols columns
+constexpr int kNwRows2CoMaxRows = 64 * 9;
+int launch_nw_rows2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 constexpr int kNwWarp2MpMaxRows = 32 * 12 * 8;  // 8 passes at most
 constexpr int kNwWarp2MpMaxCols = 2048;        // its column-sequence limit (staging buffer)
 }  // namespace dyna

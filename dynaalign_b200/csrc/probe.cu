@@ -84,11 +84,12 @@ int run_probe(double ops_per_inner, double* lane_ops_per_s, double* elapsed_ms, 
 enum OpKind { OP_IADD3 = 0, OP_VIADDMNMX, OP_VIMNMX3, OP_PRMT, OP_SELP, OP_SETP_SELP, OP_LOP3, OP_SHF, OP_IMAD,
               OP_HSET2, OP_HADD2, OP_VIADDMNMX_U16X2, OP_VIBMAX_S16X2, OP_VIMAX3_S16X2, OP_SETP_PADD, OP_SHFL,
               OP_LDS, OP_POPC, OP_VIBMAX_S32, OP_HSET2_ONLY, OP_HSET2_ISUB, OP_VIMNMX3_PRMT, OP_IMAD_PRMT,
-              OP_VIADDMNMX_ISETP, OP_IADD3_3IN, OP_HSET2_IMAD, OP_PRMT_SEL, OP_VIMNMX3_IMAD, OP_PMOV, OP_COUNT };
+              OP_VIADDMNMX_ISETP, OP_IADD3_3IN, OP_HSET2_IMAD, OP_PRMT_SEL, OP_VIMNMX3_IMAD, OP_PMOV,
+              OP_IMAD_HI, OP_DPX16_IADD, OP_DPX16_2IADD, OP_DPX16_IMADHI, OP_DPX16_IMAD, OP_IADD_IMAD, OP_DPX16_LDS128, OP_COUNT };
 
 template <int OP>
 __global__ void __launch_bounds__(kProbeThreads) op_probe_kernel(int iters, uint32_t a, uint32_t b, uint32_t* out) {
-  __shared__ uint32_t sm[kProbeThreads + 32];
+  __shared__ __align__(16) uint32_t sm[kProbeThreads + 32];
   sm[threadIdx.x] = threadIdx.x * a;
   __syncthreads();
   uint32_t x[kChains];
@@ -128,6 +129,17 @@ __global__ void __launch_bounds__(kProbeThreads) op_probe_kernel(int iters, uint
         if (OP == OP_PRMT_SEL) { asm volatile("prmt.b32 %0, %0, %1, 0x5140;" : "+r"(v) : "r"(b)); asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.b32 %0, %0, %2, p;}" : "+r"(v) : "r"(a), "r"(b)); }
         if (OP == OP_VIMNMX3_IMAD) { v = (uint32_t)__vimax3_s32((int)v, (int)a, (int)b); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(a), "r"(b)); }
         if (OP == OP_PMOV) { asm volatile("{.reg .pred p; setp.eq.u32 p, %0, %1; @p mov.u32 %0, %2;}" : "+r"(v) : "r"(b), "r"(a)); }
+        if (OP == OP_IMAD_HI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(b), "r"(a));
+        if (OP == OP_DPX16_IADD) { v = __viaddmax_s16x2(v, a, b); asm volatile("add.u32 %0, %0, %1;" : "+r"(v) : "r"(a)); }
+        if (OP == OP_DPX16_2IADD) { v = __viaddmax_s16x2(v, a, b); asm volatile("add.u32 %0, %0, %1;" : "+r"(v) : "r"(a)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v) : "r"(b)); }
+        if (OP == OP_DPX16_IMADHI) { v = __viaddmax_s16x2(v, a, b); asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(b), "r"(a)); }
+        if (OP == OP_DPX16_IMAD) { v = __viaddmax_s16x2(v, a, b); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(a), "r"(b)); }
+        if (OP == OP_IADD_IMAD) { asm volatile("add.u32 %0, %0, %1;" : "+r"(v) : "r"(a)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(a), "r"(b)); }
+        if (OP == OP_DPX16_LDS128) {  // four DPX ops per 128-bit shared load (conflict-free): does the load stream cost issue or ALU slots?
+          const uint4 q = *reinterpret_cast<const uint4*>(&sm[((threadIdx.x * 4u) + (v & 0u)) & (kProbeThreads - 4)]);
+          v = __viaddmax_s16x2(v, q.x, b); v = __viaddmax_s16x2(v, q.y, b); v = __viaddmax_s16x2(v, q.z, b); v = __viaddmax_s16x2(v, q.w, b);
+          asm volatile("" : "+r"(v));
+        }
         if (OP == OP_VIBMAX_S32) { bool p0; v = (uint32_t)__vibmax_s32((int)v, (int)a, &p0); v += (p0 ? 1u : 0u); asm volatile("" : "+r"(v)); }
       }
     }

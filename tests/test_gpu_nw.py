@@ -69,6 +69,24 @@ def test_cooperative_kernel_rows_385_to_768(R):
     check_stats(seqs)
 
 
+@pytest.mark.parametrize("lo,hi", [(33, 96), (97, 200), (201, 330), (300, 384), (33, 384)])
+def test_two_rows_kernel(lo, hi):
+    # rows i, i+1 in the two 16-bit halves against the same column sequence (nw_rows2_kernel; by default only for inputs
+    # large enough to fill the GPU with its units, forced here): adjacent rows of different and equal lengths, rows that
+    # do not pair (too different, too short, too long), odd row counts, columns of every kind
+    rng = np.random.default_rng(lo * 7 + hi)
+    fam = "".join(random_seqs(rng, 1, hi, hi, "ARNDCQEGHILKMFPSTWYV"))
+    seqs = [fam[: int(L)] for L in rng.integers(lo, hi + 1, size=40)] + random_seqs(rng, 41, lo, hi, "ARNDCQEGHILKMFPSTWYV")
+    seqs += random_seqs(rng, 6, 1, 32) + ["", fam[:hi], fam[:hi], fam[:lo]] + random_seqs(rng, 3, 385, 700)
+    rng.shuffle(seqs)
+    os.environ["DYNA_NW_ROWS2"] = "1"
+    try:
+        check_stats(seqs)
+        check_stats(seqs[:-1], "BLOSUM45", 3, 1)
+    finally:
+        del os.environ["DYNA_NW_ROWS2"]
+
+
 def test_cooperative_kernel_equals_single_warp_kernels():
     # same input through the cooperative kernel and (DYNA_NW_CO=0) the tall-strip / multi-pass kernels
     rng = np.random.default_rng(77)

@@ -77,6 +77,10 @@ def main():
     for i, ((seqs, table, go, ge), (wm, wl)) in enumerate(zip(sets, wants)):
         gm, gl = da.nw_pair_stats(seqs, table, go, ge)
         ok = (gm == wm).all() and (gl == wl).all()
+        os.environ["DYNA_NW_ROWS2"] = "1"  # the two-rows kernel is size-gated by default: force it as well
+        gm, gl = da.nw_pair_stats(seqs, table, go, ge)
+        del os.environ["DYNA_NW_ROWS2"]
+        ok = ok and (gm == wm).all() and (gl == wl).all()
         bad += 0 if ok else 1
         lens = [len(s) for s in seqs]
         print("set %2d: n=%3d len %d..%d %s go=%d ge=%d pairs=%d %s" % (i, len(seqs), min(lens), max(lens), table, go, ge, len(wm),
