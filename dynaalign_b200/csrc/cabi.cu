@@ -698,7 +698,8 @@ extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
 struct NwClass {
   int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit,
              // 6 two-pairs-per-warp 16-bit, several passes, 7 two-pairs-per-warp-pair 16-bit (cooperating warps),
-             // 8 two ROWS per warp 16-bit (units[].row and row+1 against the same column sequences), 9 its cooperative form
+             // 8 two ROWS per warp 16-bit (units[].row and row+1 against the same column sequences), 9 its cooperative form,
+             // 10 two rows per thread (short probes)
   int R;
   int64_t work = 0;  // DP cells of the class (launch order: largest first)
   std::vector<NwUnit> units;
@@ -813,6 +814,9 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // (its units are two rows x 256 columns on a whole SM: only for inputs large enough to fill the GPU with them)
   bool use_rows2 = p->pairs >= (int64_t)kNwWarp2UnitColsMax * kNwMultiPassGrid * 32;
   if (const char* e = getenv("DYNA_NW_ROWS2")) use_rows2 = atoi(e) != 0;
+  // short probes (rows <= 32 residues): two rows per thread; DYNA_NW_TROWS2=0 restores one row against two columns
+  bool use_trows2 = pack16;
+  if (const char* e = getenv("DYNA_NW_TROWS2")) use_trows2 = use_trows2 && atoi(e) != 0;
   // the cooperative form of the same (row pairs of 385..576 residues).  Units of 128 columns also on small inputs
   // (BASELINE config 2: 3337 GCUPS against 3291 at 64 and 3207 at 32 columns)
   bool use_rows2co = use_co;
@@ -879,11 +883,25 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   for (int64_t i = 0; i < n; ++i) len_prefix[(size_t)i + 1] = len_prefix[(size_t)i] + (offsets[i + 1] - offsets[i]);
   for (int64_t i = row_begin; i < row_end; ++i) {
     const int m = (int)(offsets[i + 1] - offsets[i]);
-    if ((use_rows2 || use_rows2co) && !force_warp2 && i + 1 < row_end) {
+    if ((use_rows2 || use_rows2co || use_trows2) && !force_warp2 && i + 1 < row_end) {
       // two-rows kernel: both rows in the single-pass packed range, similar length (the strip layout follows the longer
       // one), and EVERY column sequence they meet within the 16-bit value range and the staging buffer
       const int m2 = (int)(offsets[i + 2] - offsets[i + 1]);
       const int mx = std::max(m, m2), mn = std::min(m, m2);
+      if (use_trows2 && mn >= 1 && mx <= kNwThreadMaxRows) {
+        // short probes: two rows per thread (nw_thread_rows2_kernel)
+        const int64_t nmax = range_max(i, n);
+        if (fits16u(mx, nmax)) {
+          NwClass* cls = get_class(10, nw_thread_R(mx));
+          for (int64_t j = i; j < n; j += 2 * kNwThreadUnitPairs) {
+            const int64_t cnt = std::min<int64_t>(2 * kNwThreadUnitPairs, n - j);
+            cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
+            cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
+          }
+          ++i;
+          continue;
+        }
+      }
       if (use_rows2co && mn >= kNwCoMinRows && mx <= kNwRows2CoMaxRows && nw_co_R(mx) >= 7 && (mn - 1) / (32 * nw_co_R(mx)) == 1) {
         // cooperative form: both rows reach into the second warp's block of 32*R rows
         const int64_t nmax = range_max(i, n);
@@ -1038,6 +1056,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       case 7: DYNA_TRY(launch_nw_warp2co(c->R, d, c->d_units.p, nu, cs)); break;
       case 8: DYNA_TRY(launch_nw_rows2(c->R, d, c->d_units.p, nu, cs)); break;
       case 9: DYNA_TRY(launch_nw_rows2co(c->R, d, c->d_units.p, nu, cs)); break;
+      case 10: DYNA_TRY(launch_nw_thread_rows2(c->R, d, c->d_units.p, nu, cs)); break;
       default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, cs)); break;
     }
     ++p->launches;

@@ -1864,6 +1864,130 @@ nw_thread2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4x2 "two rows": one thread per column sequence, the two 16-bit halves carry rows i and i+1 (both <= 32 residues) --
+// the short-probe counterpart of nw_rows2_kernel.  Every thread of the CTA aligns the same two row sequences, so the
+// table has no lane dimension: per residue class and strip row three words (packed scores, increment of pair 1,
+// increment of pair 2), class stride odd, so that the 32 lanes of a warp -- each at its own column residue -- read
+// conflict-free 32-bit words (equal classes broadcast).  Against nw_thread2_kernel (one row, two column sequences) a
+// row costs three shared loads instead of one load and three PRMT: 5 instead of 8 ALU-pipe instructions per row, the
+// pipe that kernel saturates (ncu r01d: ALU 78 %).
+// ------------------------------------------------------------------------------------------------
+// one column of the two-rows thread kernel: rows 0..R-1 of both row sequences against column residue class `base`
+template <int R>
+__device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
+                                                    const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
+                                                    uint32_t (&SBn)[R], uint32_t base, uint32_t diagH, uint32_t F, uint32_t ngo2,
+                                                    const Stat2Consts& c) {
+  uint32_t dSA = 0u, dSB = 0u, upSA = 0u, upSB = 0u;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t sP = lds_u32(base + 12u * (unsigned)k);
+    const uint32_t incA = lds_u32(base + 12u * (unsigned)k + 4u);
+    const uint32_t incB = lds_u32(base + 12u * (unsigned)k + 8u);
+    const uint32_t E = El[k];
+    const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    bool puB, puA, pdB, pdA;
+    const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);
+    const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    const uint32_t SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
+    diagH = Ho[k];
+    dSA = SAo[k];
+    dSB = SBo[k];
+    Hn[k] = H;
+    SAn[k] = SA;
+    SBn[k] = SB;
+    El[k] = __viaddmax_s16x2(H, ngo2, E);
+    F = __viaddmax_s16x2(H, ngo2, F);
+    upSA = SA;
+    upSB = SB;
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreadThreads, R <= 16 ? 4 : 1)
+nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
+  constexpr int TS = (3 * R) | 1;  // words per residue class (odd: conflict-free across classes)
+  __shared__ uint32_t tab[24 * TS];
+  const int tid = threadIdx.x;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.zero;
+  const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // register operand (see nw_thread2_kernel)
+  const uint32_t bord2 = pack16(ge - go);
+  const uint32_t tab_sh = (uint32_t)__cvta_generic_to_shared(tab);
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const NwUnit un = units[u];
+    const int row = un.row, row2 = un.row + 1;
+    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
+    const uint8_t* __restrict__ a1 = d.codes + d.off[row];
+    const uint8_t* __restrict__ a2 = d.codes + d.off[row2];
+    __syncthreads();
+    for (int idx = tid; idx < 24 * TS; idx += kThreadThreads) {
+      const int cls = idx / TS, w = idx - cls * TS;
+      uint32_t v = 0u;
+      if (w < 3 * R) {
+        const int k = w / 3, t = w - 3 * k;
+        if (t == 0) {
+          const int s1 = k < m1 ? (int)(int8_t)(d.sub[a1[k] * 24 + cls] + 2 * ge) : 0;
+          const int s2 = k < m2 ? (int)(int8_t)(d.sub[a2[k] * 24 + cls] + 2 * ge) : 0;
+          v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
+        } else if (t == 1) {
+          v = 1u | ((k < m1 && a1[k] == cls) ? 0x10000u : 0u);
+        } else {
+          v = 1u | ((k < m2 && a2[k] == cls) ? 0x10000u : 0u);
+        }
+      }
+      tab[idx] = v;
+    }
+    __syncthreads();
+    for (int jj = tid; jj < un.j_count; jj += kThreadThreads) {
+      const int j = un.j_begin + jj;
+      const int n = d.off[j + 1] - d.off[j];
+      const uint8_t* __restrict__ b = d.codes + d.off[j];
+      uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        H0[k] = H1[k] = bord2;
+        El[k] = sent2;
+        SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+      }
+      uint32_t diag0 = 0u;  // corner (0,0); the border row (slanted: -go + ge) for every later column
+      for (int t0 = 0; t0 < n; t0 += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const int t = t0 + ph;
+          if (t < n) {
+            const uint32_t base = tab_sh + (uint32_t)b[t] * (uint32_t)(TS * 4);
+            if (ph == 0) thread_rows2_column<R>(H0, H1, El, SA0, SA1, SB0, SB1, base, diag0, sent2, ngo2, c);
+            else thread_rows2_column<R>(H1, H0, El, SA1, SA0, SB1, SB0, base, diag0, sent2, ngo2, c);
+            diag0 = bord2;
+          }
+        }
+      }
+      const bool in1 = ((n & 1) != 0);
+      uint32_t resA = 0u, resB = 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (k == m1 - 1) resA = in1 ? SA1[k] : SA0[k];
+        if (k == m2 - 1) resB = in1 ? SB1[k] : SB0[k];
+      }
+      const int64_t slot1 = pair_slot(d.n, row, j, d.slab_base);
+      d.matches[slot1] = resA >> 16;
+      d.length[slot1] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
+      if (j >= row2) {  // column `row` exists for the first row only
+        const int64_t slot2 = pair_slot(d.n, row2, j, d.slab_base);
+        d.matches[slot2] = resB >> 16;
+        d.length[slot2] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+      }
+    }
+  }
+}
+
 // rows of length 0: no DP; the path is n left moves -> matches 0, length n (0/0 -> NaN handled at the division)
 __global__ void nw_empty_rows_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -2082,6 +2206,22 @@ int launch_nw_thread2(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 #undef DYNA_CASE
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw thread2 kernel: unsupported strip height %d", R);
+  }
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_thread_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  switch (R) {
+#define DYNA_CASE(RR)                                                                        \
+  case RR:                                                                                   \
+    nw_thread_rows2_kernel<RR><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units); \
+    break;
+    DYNA_CASE(4) DYNA_CASE(8) DYNA_CASE(12) DYNA_CASE(16) DYNA_CASE(20) DYNA_CASE(24) DYNA_CASE(28) DYNA_CASE(32)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw thread two-rows kernel: unsupported strip height %d", R);
   }
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;

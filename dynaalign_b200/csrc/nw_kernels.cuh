@@ -51,6 +51,9 @@ int launch_nw_warp(int R, bool slant, bool multipass, const NwDeviceData& d, con
 // two pairs per warp in 16-bit lanes (host guarantees the value range); R in 2..kNwWarp2MaxR
 int launch_nw_warp2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 int launch_nw_thread2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
+// two rows (units[].row and row+1, both <= 32 residues) per thread against one column sequence each; units of up to
+// 2 * kNwThreadUnitPairs columns
+int launch_nw_thread_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 // packed kernel, several passes of 32*R rows (R in 7..12); scratch: kNwMultiPassGrid * 32 pair-sets * kNwWarp2MpMaxCols * 16 bytes
 int launch_nw_warp2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, void* d_scratch, cudaStream_t st);
 // cooperative packed kernel: two warps share one 64-lane wavefront (rows 385..768, R = ceil(m/64) in 7..12, so that the

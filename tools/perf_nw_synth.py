@@ -7,8 +7,11 @@ sys.path.insert(0, ROOT)
 from dynaalign_b200 import synth
 from dynaalign_b200._lib import check, flatten, lib, ptr
 L = lib()
+kind = "proteins"
+if ":" in sys.argv[1]:
+    kind, sys.argv[1] = sys.argv[1].split(":")
 n = int(sys.argv[1])
-seqs = synth.proteins_families(20000)[:n]
+seqs = synth.proteins_families(20000)[:n] if kind == "proteins" else synth.peptides_uniform(n, length=int(kind[3:] or 16))
 res, off = flatten(seqs)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 ref = None
