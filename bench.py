@@ -21,7 +21,7 @@ Metric (BASELINE.json): NW all-pairs GCUPS and MinHash pairs/s.  One JSON line o
     counts (plus the count histogram), summed over ranks and compared with tests/golden/bench_checksums.json
     (written by `bench.py --write-golden` on one GPU).  A partition that loses or repeats a row changes the sum.
     A mismatch makes the process exit non-zero.
-  * `roofline`: for the dominant kernel (nw_warp_kernel): algorithmic integer ops (11 per DP cell)
+  * `roofline`: for the dominant kernel (nw_rows2_kernel): algorithmic integer ops (11 per DP cell)
     per second against the INT32 issue peak measured live with dyna_probe_int_issue (MEASURED_PEAKS.json has no
     integer figure).  The MinHash match kernel reports the HBM roofline BASELINE.json names (2.04 B/pair) and the
     integer one that actually binds it.
@@ -589,7 +589,7 @@ def phase_target_nw(ctx):
     del out_m, out_l
     ctx.release_memory()
     return {"n": n, "pairs": int(pairs), "cells": int(cells), "seconds": ms * 1e-3, "gcups": cells / (ms * 1e-3) / 1e9,
-            "kernel": "nw_thread2_kernel", "checksum": checksum,
+            "kernel": "nw_thread_rows2_kernel", "checksum": checksum,
             "e2e": {"seconds": e2e_s, "gcups": cells / e2e_s / 1e9, "d2h_bytes_per_step": int(2 * my_pairs),
                     "api": "dyna_nw_pair_stats8 per rank: validate + encode + plan + H2D + kernel + u8 pack + D2H of 2 bytes per pair "
                            "(matches, length <= 32), pinned host buffers"},
@@ -786,15 +786,16 @@ def main():
                          "issue_active_pct": kmet.get("smsp__issue_active_pct"), "alu_pipe_pct": kmet.get("sm__pipe_alu_pct"),
                          "shared_wavefronts_pct": kmet.get("l1tex_shared_wavefronts_pct"),
                          "utilisation_note": kmet.get("note"),
-                         "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (nw_warp2_kernel<11>, "
-                                          "%.3g pairs of this workload), profiles/r01d_nw_config5_traffic.csv; algorithmic %.3g B"
-                                          % (tinfo["nw_config5_dominant_launch"]["pairs_upper_bound"],
+                         "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (%s, <= %.3g pairs of this "
+                                          "workload), %s; algorithmic %.3g B"
+                                          % (tinfo["nw_config5_dominant_launch"]["kernel"], tinfo["nw_config5_dominant_launch"]["pairs_upper_bound"],
+                                             tinfo["nw_config5_dominant_launch"]["source"].split(":")[0],
                                              tinfo["nw_config5_dominant_launch"]["algorithmic_bytes"])) if traffic else None,
                          "traffic_reduced_capture": {"dram_bytes": tinfo.get("nw_warp_kernel_dram_bytes_per_launch"),
                                                      "kernel": tinfo.get("nw_warp_kernel_dram_bytes_per_launch_kernel"),
                                                      "grid": tinfo.get("nw_warp_kernel_dram_bytes_per_launch_grid"),
                                                      "note": "ncu --set full, NW n=700 (0.27e11 cells): inputs stay in L2, DRAM traffic is negligible by construction"},
-                         "note": "dominant kernel nw_warp2_kernel (16-bit DPX, two pairs per warp): neither HBM- nor tensor-bound; 11 algorithmic integer ops per DP cell "
+                         "note": "dominant kernel nw_rows2_kernel (16-bit DPX, two row sequences per warp against one column sequence): neither HBM- nor tensor-bound; 11 algorithmic integer ops per DP cell "
                                  "(SURVEY.md 8(d)) against the INT32 issue peak measured live by dyna_probe_int_issue (IADD3 chains); the packed kernel "
                                  "updates two cells per instruction, so frac is not a ceiling -- issue_active_pct / alu_pipe_pct are the utilisation"},
             "cpu_baseline": cpu,
