@@ -435,9 +435,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // A lost TMA must fault loudly instead of hanging the GPU -- but only a genuinely lost one: the watchdog is a wall-
+  // clock bound (20 s on %globaltimer, read once per 2^16 failed polls), so preemption, MPS time slicing or a debugger
+  // stopping the context for a while cannot trip it the way a poll count could.
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();  // a lost TMA must fault loudly, never hang the GPU
+    if ((++spins & 0xFFFFu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
