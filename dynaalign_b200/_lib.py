@@ -78,6 +78,12 @@ _SIGS = {
     "dyna_nw_plan_fetch": (C.c_int, [C.c_void_p, _u32p, _u32p, C.c_void_p]),
     "dyna_nw_plan_fetch_packed8": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_void_p]),
     "dyna_nw_plan_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "dyna_nw_plan_max_len": (C.c_int, [C.c_void_p]),
+    "dyna_nw_plan_stat_histogram": (C.c_int, [C.c_void_p, _i32p, C.c_int64, C.POINTER(C.c_uint64), C.c_void_p]),
+    "dyna_nw_plan_fetch_diagonal": (C.c_int, [C.c_void_p, _i32p, C.c_int64, _u32p, _u32p, C.c_void_p]),
+    "dyna_quantile_type7_identities": (C.c_int, [C.POINTER(C.c_uint64), C.c_int64, C.c_int64, C.c_double, _f64p]),
+    "dyna_nw_plan_threshold_edges": (C.c_int, [C.c_void_p, _i32p, C.c_int64, C.c_double, C.c_int64, _i32p, _i32p, _u32p, _u32p,
+                                              _i64p, C.c_void_p]),
     "dyna_nw_plan_pairs": (C.c_int64, [C.c_void_p]),
     "dyna_nw_plan_cells": (C.c_int64, [C.c_void_p]),
     "dyna_nw_plan_launches": (C.c_int, [C.c_void_p]),

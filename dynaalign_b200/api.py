@@ -24,7 +24,7 @@ from ._lib import DynaAlignError, check, flatten, lib, ptr
 __all__ = ["similarityMH", "similarityNW", "shingle", "create_vocab", "create_char_matrix", "create_hash_parameters",
            "apply_hash", "compute_signature_matrix", "compute_distance_matrix", "minhash", "dimnames",
            "hashfamily_seeds", "mh_signatures", "mh_match_counts", "nw_pair_stats", "partition_rows",
-           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "MinHashPlan", "NWPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError",
+           "substitution_matrix", "quantile_type7_counts", "similarityMH_edges", "similarityNW_edges", "quantile_type7_identities", "MinHashPlan", "NWPlan", "vocab_ranks", "minhash_gpu", "DynaAlignError",
            "nw_pair_stats8", "checksum", "checksum_weights"]
 
 
@@ -169,6 +169,35 @@ def quantile_type7_counts(hist, n_hash, prob):
     thr, mc = C.c_double(0), C.c_int(0)
     check(lib().dyna_quantile_type7_counts(ptr(hist, C.c_uint64), int(n_hash), float(prob), C.byref(thr), C.byref(mc)))
     return thr.value, mc.value
+
+
+def quantile_type7_identities(hist, prob):
+    """quantile(matches / length, prob, type = 7) from a (matches, length) histogram [max_len + 1, 2 max_len + 1]."""
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    thr = C.c_double(0)
+    check(lib().dyna_quantile_type7_identities(ptr(hist, C.c_uint64), hist.shape[0], hist.shape[1], float(prob), C.byref(thr)))
+    return thr.value
+
+
+def identities_at_least(hist, threshold):
+    """Number of histogram pairs with 0 < matches / length >= threshold (the exact size of the edge list)."""
+    hist = np.asarray(hist)
+    m = np.arange(hist.shape[0], dtype=np.float64)[:, None]
+    l = np.arange(hist.shape[1], dtype=np.float64)[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        keep = (m > 0) & (l > 0) & (m / l >= threshold)
+    return int(hist[keep].sum())
+
+
+def similarityNW_edges(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, thresh_p=0.8, *, device=0):
+    """similarityNW followed by clusterbreak's thresholding (R/clusterbreak.R:217-221) without the dense n x n matrix.
+    Returns (threshold, i, j, weight) with 0-based i < j in row-major order and weight = matches / alignment_length."""
+    plan = NWPlan(sequences, matrixName, gapOpen, gapExt, device=device)
+    try:
+        plan.run()
+        return plan.threshold_edges(thresh_p)
+    finally:
+        plan.close()
 
 
 def similarityMH_edges(sequences, k=4, n_hash=50, thresh_p=0.8, *, seed=None, seeds=None, device=0):
@@ -355,6 +384,58 @@ class NWPlan:
         h = (C.c_uint64 * 2)()
         check(lib().dyna_nw_plan_checksum(self._h, h, None))
         return int(h[0]), int(h[1])
+
+    # ---- threshold + sparsify (clusterbreak's next step, R/clusterbreak.R:217-221) on the computed triangle
+    max_len = property(lambda self: lib().dyna_nw_plan_max_len(self._h))
+
+    @staticmethod
+    def _members(members):
+        if members is None:
+            return None, None, 0
+        m = np.ascontiguousarray(members, dtype=np.int32)
+        return m, ptr(m, C.c_int32), len(m)
+
+    def stat_histogram(self, members=None):
+        """uint64[max_len + 1, 2 max_len + 1] counts of (matches, length) over the strict upper triangle of the node
+        (`members`: strictly increasing 0-based indices, None = all sequences) within the plan's row range."""
+        ml = self.max_len
+        hist = np.zeros((ml + 1, 2 * ml + 1), dtype=np.uint64)
+        _keep, mp, nm = self._members(members)
+        check(lib().dyna_nw_plan_stat_histogram(self._h, mp, nm, ptr(hist, C.c_uint64), None))
+        return hist
+
+    def diagonal(self, members=None):
+        """(matches, length) of the node's self-alignments: sim[i, i], the self-loop weights netcluster's graph carries."""
+        _keep, mp, nm = self._members(members)
+        cnt = self.n if members is None else nm
+        mt = np.zeros(max(cnt, 1), dtype=np.uint32)
+        ln = np.zeros(max(cnt, 1), dtype=np.uint32)
+        check(lib().dyna_nw_plan_fetch_diagonal(self._h, mp, nm, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32), None))
+        return mt[:cnt], ln[:cnt]
+
+    def edges_at(self, threshold, capacity, members=None):
+        """Pairs a < b of the node with 0 < (double)matches/length >= threshold: (i, j, matches, length), row-major,
+        node-local 0-based indices."""
+        _keep, mp, nm = self._members(members)
+        cap = max(int(capacity), 1)
+        ei = np.zeros(cap, dtype=np.int32)
+        ej = np.zeros(cap, dtype=np.int32)
+        em = np.zeros(cap, dtype=np.uint32)
+        el = np.zeros(cap, dtype=np.uint32)
+        ne = C.c_int64(0)
+        check(lib().dyna_nw_plan_threshold_edges(self._h, mp, nm, float(threshold), int(capacity), ptr(ei, C.c_int32),
+                                                 ptr(ej, C.c_int32), ptr(em, C.c_uint32), ptr(el, C.c_uint32), C.byref(ne), None))
+        k = ne.value
+        return ei[:k], ej[:k], em[:k], el[:k]
+
+    def threshold_edges(self, thresh_p, members=None):
+        """(threshold, i, j, weight): quantile(sim[upper.tri(sim)], thresh_p) (type 7, exact) and the pairs that survive
+        `sim[sim < threshold] <- 0` with a non-zero similarity; weight = matches / length as the reference computes it."""
+        hist = self.stat_histogram(members)
+        thr = quantile_type7_identities(hist, thresh_p)
+        cap = identities_at_least(hist, thr)
+        ei, ej, em, el = self.edges_at(thr, cap, members)
+        return thr, ei, ej, em.astype(np.float64) / el.astype(np.float64)
 
     def close(self):
         if getattr(self, "_h", None):

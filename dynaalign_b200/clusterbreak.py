@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from .api import MinHashPlan, RError
+from .api import MinHashPlan, NWPlan, RError
 
 
 def connected_components(n, i, j, weight=None):
@@ -42,12 +42,13 @@ def netcluster_edges(n, ei, ej, weight, cluster_fn, cluster_wt=True, diag_weight
 
     The reference builds graph_from_adjacency_matrix(pepmat, mode = "upper", weighted = TRUE): one edge per non-zero
     entry of the upper triangle INCLUDING the diagonal, so every vertex carries a self-loop of weight sim[i, i]
-    (1.0 for similarityMH, src/minHash.cpp:161).  The same graph is handed to `cluster_fn` here.
+    (1.0 for similarityMH, src/minHash.cpp:161; `diag_weight` may be a vector: the self-alignment identities of
+    similarityNW).  The same graph is handed to `cluster_fn` here.
     """
     loops = np.arange(n, dtype=np.int64)
     gi = np.concatenate([loops, np.asarray(ei, dtype=np.int64)])
     gj = np.concatenate([loops, np.asarray(ej, dtype=np.int64)])
-    gw = np.concatenate([np.full(n, float(diag_weight)), np.asarray(weight, dtype=np.float64)])
+    gw = np.concatenate([np.broadcast_to(np.asarray(diag_weight, dtype=np.float64), (n,)), np.asarray(weight, dtype=np.float64)])
     out = cluster_fn(n, gi, gj, gw) if cluster_wt else cluster_fn(n, gi, gj, None)
     try:
         out = np.asarray(out)
@@ -59,13 +60,42 @@ def netcluster_edges(n, ei, ej, weight, cluster_fn, cluster_wt=True, diag_weight
     return out.astype(np.int64)
 
 
+class _NWNode:
+    """A clusterbreak recursion node over ONE computed NW triangle.  similarityNW(sub-cluster) is the sub-matrix of the
+    root's similarity matrix for the members in their original order (pair results do not depend on the other sequences,
+    and the row sequence of a pair is still the lower-index one), so a node is only a member list: its histogram,
+    threshold, edges and self-loop weights are read off the root's slab on the device and nothing is re-aligned -- the
+    reference re-runs the whole O(n^2) alignment at every node (R/clusterbreak.R:217, :250-254)."""
+
+    def __init__(self, plan, members=None, owner=True):
+        self.plan, self.members, self.owner = plan, members, owner
+
+    def threshold_edges(self, thresh_p):
+        return self.plan.threshold_edges(thresh_p, self.members)
+
+    def diag_weight(self):
+        m, l = self.plan.diagonal(self.members)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return m.astype(np.float64) / l.astype(np.float64)  # NaN for an empty sequence, as src/pairwiseSeqAlign.cpp:311
+
+    def subset(self, local):
+        base = np.arange(self.plan.n, dtype=np.int32) if self.members is None else self.members
+        return _NWNode(self.plan, np.ascontiguousarray(base[np.asarray(local, dtype=np.int64)], dtype=np.int32), owner=False)
+
+    def close(self):
+        if self.owner:
+            self.plan.close()
+
+
 def _log(msg, level="INFO", stream=None):
     print("[%s] %s: %s" % (time.strftime("%H:%M:%S"), level, msg), file=stream or sys.stdout)
 
 
 def clusterbreak(pep, cluster_fn, thresh_p=0.8, size_max=10, size_min=3, max_itr=10000, k=2, n_hash=50, seed=None,
-                 seeds=None, cluster_wt=True, device=0, verbose=True):
-    """clusterbreak (R/clusterbreak.R:180-275) with sim_fn = similarityMH(k, n_hash) kept on the device.
+                 seeds=None, cluster_wt=True, device=0, verbose=True, sim="MH", matrixName="BLOSUM62", gapOpen=10, gapExt=4):
+    """clusterbreak (R/clusterbreak.R:180-275) with sim_fn kept on the device: sim = "MH" is similarityMH(k, n_hash)
+    (the reference's default sim_fn), sim = "NW" is similarityNW(matrixName, gapOpen, gapExt), aligned ONCE for the
+    whole input (every recursion node reads its sub-matrix of that triangle, see _NWNode).
 
     Same control flow as the reference: one call of `sim_fn` per recursion node, type-7 quantile threshold, clusters
     larger than `size_max` are re-clustered (depth first, in order of first appearance), clusters smaller than
@@ -83,7 +113,12 @@ def clusterbreak(pep, cluster_fn, thresh_p=0.8, size_max=10, size_min=3, max_itr
     if len(pep) == 0:
         raise RError("empty input sequence vector")
     state = {"rows": [], "itr": 1, "convergence": 1, "filtered": []}
-    root = MinHashPlan(pep, k, n_hash, seed=seed, seeds=seeds, device=device)
+    if sim == "MH":
+        root = MinHashPlan(pep, k, n_hash, seed=seed, seeds=seeds, device=device)
+    elif sim == "NW":
+        root = _NWNode(NWPlan(pep, matrixName, gapOpen, gapExt, device=device).run())
+    else:
+        raise RError("sim must be 'MH' or 'NW'")
 
     def recurse(plan, members):
         # `members`: indices into `pep` of this node's sequences, in the node's own order
@@ -98,7 +133,9 @@ def clusterbreak(pep, cluster_fn, thresh_p=0.8, size_max=10, size_min=3, max_itr
             w = np.zeros(0)
         else:
             _, ei, ej, w = plan.threshold_edges(thresh_p)
-        c_index = netcluster_edges(n, ei, ej, w, cluster_fn, cluster_wt)
+        # self-loops: 1.0 for similarityMH (src/minHash.cpp:161), the computed self-alignment identity for similarityNW
+        dw = plan.diag_weight() if sim == "NW" else 1.0
+        c_index = netcluster_edges(n, ei, ej, w, cluster_fn, cluster_wt, diag_weight=dw)
         c_size = np.bincount(c_index[c_index > 0], minlength=1)[1:]  # tabulate(): ids 1..max
         ids = np.arange(1, len(c_size) + 1)
         id_itr = ids[c_size > size_max]

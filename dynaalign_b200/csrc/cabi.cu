@@ -18,6 +18,7 @@
 #include "gather.cuh"
 #include "mh_kernels.cuh"
 #include "nw_kernels.cuh"
+#include "nw_post.cuh"
 
 using namespace dyna;
 
@@ -1119,6 +1120,167 @@ extern "C" int dyna_nw_plan_fetch_packed8(dyna_nw_plan* p, uint8_t* matches8_out
   DYNA_TRY(launch_nw_pack8(p->matches.p, p->length.p, p->pairs, m8.p, l8.p, st));
   DYNA_CUDA(cudaMemcpyAsync(matches8_out, m8.p, (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaMemcpyAsync(length8_out, l8.p, (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
+// ---- threshold + sparsify for sim_fn = similarityNW (R/clusterbreak.R:217-221); kernels in nw_post.cu
+extern "C" int dyna_nw_plan_max_len(const dyna_nw_plan* p) { return p ? p->max_cols : 0; }
+
+namespace {
+constexpr int64_t kNwHistMaxBins = 1ll << 27;  // 1 GB of u64 bins: sequences up to ~8,000 residues
+
+// node description of a plan; uploads the member list (strictly increasing plan indices) when there is one
+int nw_make_node(dyna_nw_plan* p, const int32_t* members, int64_t n_members, DevBuf<int32_t>& d_members, cudaStream_t st,
+                 NwNode* nd, const char* who) {
+  nd->matches = p->matches.p;
+  nd->length = p->length.p;
+  nd->n = p->n;
+  nd->row_begin = p->row_begin;
+  nd->row_end = p->row_end;
+  nd->slab_base = tri_diag_rows(p->n, p->row_begin);
+  nd->members = nullptr;
+  nd->n_node = p->n;
+  if (!members) return DYNA_OK;
+  if (n_members < 0) return fail(DYNA_ERR_INVALID, "%s: negative member count", who);
+  for (int64_t t = 0; t < n_members; ++t)
+    if (members[t] < 0 || members[t] >= p->n || (t > 0 && members[t] <= members[t - 1]))
+      return fail(DYNA_ERR_INVALID, "%s: members must be strictly increasing indices in [0, %lld) (members[%lld] = %d)", who,
+                  (long long)p->n, (long long)t, (int)members[t]);
+  DYNA_TRY(d_members.alloc((size_t)n_members));
+  if (n_members > 0)
+    DYNA_CUDA(cudaMemcpyAsync(d_members.p, members, sizeof(int32_t) * (size_t)n_members, cudaMemcpyHostToDevice, st));
+  nd->members = d_members.p;
+  nd->n_node = n_members;
+  return DYNA_OK;
+}
+}  // namespace
+
+// hist_out: (max_len + 1) x (2 max_len + 1) counters, row-major [matches][length], over the strict upper triangle of the
+// node (pairs a < b of `members`, or of all sequences when members == NULL) restricted to the plan's row range
+extern "C" int dyna_nw_plan_stat_histogram(dyna_nw_plan* p, const int32_t* members, int64_t n_members, uint64_t* hist_out,
+                                           void* stream) {
+  if (!p || !hist_out) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_stat_histogram: null argument");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  const int64_t mdim = (int64_t)p->max_cols + 1, ldim = 2 * (int64_t)p->max_cols + 1;
+  if (mdim * ldim > kNwHistMaxBins)
+    return fail(DYNA_ERR_UNSUPPORTED, "dyna_nw_plan_stat_histogram: %lld x %lld (matches, length) bins exceed the supported %lld",
+                (long long)mdim, (long long)ldim, (long long)kNwHistMaxBins);
+  DevBuf<int32_t> d_members;
+  NwNode nd;
+  DYNA_TRY(nw_make_node(p, members, n_members, d_members, st, &nd, "dyna_nw_plan_stat_histogram"));
+  DevBuf<unsigned long long> d_hist;
+  DYNA_TRY(d_hist.alloc((size_t)(mdim * ldim)));
+  DYNA_TRY(launch_nw_stat_hist(nd, mdim, ldim, d_hist.p, st));
+  DYNA_CUDA(cudaMemcpyAsync(hist_out, d_hist.p, sizeof(uint64_t) * (size_t)(mdim * ldim), cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  return DYNA_OK;
+}
+
+// (matches, length) of the node's self-alignments -- the diagonal of the similarity matrix, which
+// graph_from_adjacency_matrix(mode = "upper") turns into self-loops (R/clusterbreak.R:122-124); zeros for rows outside
+// the plan's row range, so ranks can add their outputs
+extern "C" int dyna_nw_plan_fetch_diagonal(dyna_nw_plan* p, const int32_t* members, int64_t n_members, uint32_t* matches_out,
+                                           uint32_t* length_out, void* stream) {
+  if (!p || !matches_out || !length_out) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_fetch_diagonal: null argument");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  DevBuf<int32_t> d_members;
+  NwNode nd;
+  DYNA_TRY(nw_make_node(p, members, n_members, d_members, st, &nd, "dyna_nw_plan_fetch_diagonal"));
+  if (nd.n_node > 0) {
+    DevBuf<uint32_t> dm, dl;
+    DYNA_TRY(dm.alloc((size_t)nd.n_node));
+    DYNA_TRY(dl.alloc((size_t)nd.n_node));
+    DYNA_TRY(launch_nw_diag(nd, dm.p, dl.p, st));
+    DYNA_CUDA(cudaMemcpyAsync(matches_out, dm.p, sizeof(uint32_t) * (size_t)nd.n_node, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaMemcpyAsync(length_out, dl.p, sizeof(uint32_t) * (size_t)nd.n_node, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaStreamSynchronize(st));
+  }
+  return DYNA_OK;
+}
+
+// R's quantile(x, prob, type = 7) (R/clusterbreak.R:219) for x = (double)matches / (double)length with the multiplicities of
+// a (matches, length) histogram; several ranks' histograms are simply added before the call
+extern "C" int dyna_quantile_type7_identities(const uint64_t* hist, int64_t mdim, int64_t ldim, double prob, double* threshold_out) {
+  if (!hist || mdim <= 0 || ldim <= 0) return fail(DYNA_ERR_INVALID, "dyna_quantile_type7_identities: bad histogram");
+  if (!(prob >= 0.0 && prob <= 1.0)) return fail(DYNA_ERR_INVALID, "'probs' outside [0,1]");
+  if (hist[0] != 0)  // two empty sequences: 0/0 = NaN in the reference's matrix (src/pairwiseSeqAlign.cpp:311)
+    return fail(DYNA_ERR_INVALID, "missing values and NaN's not allowed if 'na.rm' is FALSE");
+  std::vector<std::pair<double, uint64_t>> v;
+  for (int64_t m = 0; m < mdim; ++m)
+    for (int64_t l = 1; l < ldim; ++l)
+      if (const uint64_t c = hist[m * ldim + l]) v.emplace_back((double)m / (double)l, c);
+  if (v.empty()) return fail(DYNA_ERR_INVALID, "quantile of an empty set of pairs");
+  std::sort(v.begin(), v.end());
+  long double total = 0;
+  for (const auto& e : v) total += (long double)e.second;
+  const double N = (double)total;
+  const double index = 1.0 + std::max(N - 1.0, 0.0) * prob;
+  const double lo = std::floor(index), hi = std::ceil(index);
+  auto value_at_rank = [&](double r) {  // r-th smallest, 1-based
+    long double cum = 0;
+    for (const auto& e : v) {
+      cum += (long double)e.second;
+      if ((double)cum >= r) return e.first;
+    }
+    return v.back().first;
+  };
+  double qs = value_at_rank(lo);
+  const double xhi = value_at_rank(hi);
+  if (index > lo && xhi != qs) {
+    const double h = index - lo;
+    qs = (1.0 - h) * qs + h * xhi;
+  }
+  if (threshold_out) *threshold_out = qs;
+  return DYNA_OK;
+}
+
+// the pairs a < b of the node that survive `sim[sim < threshold] <- 0` with a non-zero similarity, row-major, as
+// node-local 0-based indices plus (matches, length); weight = (double)matches / length
+extern "C" int dyna_nw_plan_threshold_edges(dyna_nw_plan* p, const int32_t* members, int64_t n_members, double threshold,
+                                            int64_t max_edges, int32_t* i_out, int32_t* j_out, uint32_t* matches_out,
+                                            uint32_t* length_out, int64_t* n_edges_out, void* stream) {
+  if (!p) return fail(DYNA_ERR_INVALID, "null plan");
+  if (threshold != threshold) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_threshold_edges: threshold is NaN");
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  if (n_edges_out) *n_edges_out = 0;
+  DevBuf<int32_t> d_members;
+  NwNode nd;
+  DYNA_TRY(nw_make_node(p, members, n_members, d_members, st, &nd, "dyna_nw_plan_threshold_edges"));
+  if (nd.n_node < 2 || p->pairs <= 0) {
+    DYNA_CUDA(cudaStreamSynchronize(st));
+    return DYNA_OK;
+  }
+  DevBuf<unsigned long long> rc, ro, tot;
+  DYNA_TRY(rc.alloc((size_t)nd.n_node));
+  DYNA_TRY(ro.alloc((size_t)nd.n_node));
+  DYNA_TRY(tot.alloc(1));
+  DYNA_TRY(launch_nw_edges_count(nd, threshold, rc.p, ro.p, tot.p, st));
+  unsigned long long total = 0;
+  DYNA_CUDA(cudaMemcpyAsync(&total, tot.p, sizeof total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  if (n_edges_out) *n_edges_out = (int64_t)total;
+  if ((int64_t)total > max_edges)
+    return fail(DYNA_ERR_INVALID, "edge buffer too small: %lld edges, capacity %lld", (long long)total, (long long)max_edges);
+  if (total == 0) return DYNA_OK;
+  if (!i_out || !j_out || !matches_out || !length_out) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_threshold_edges: null output");
+  DevBuf<int32_t> di, dj;
+  DevBuf<uint32_t> dm, dl;
+  DYNA_TRY(di.alloc((size_t)total));
+  DYNA_TRY(dj.alloc((size_t)total));
+  DYNA_TRY(dm.alloc((size_t)total));
+  DYNA_TRY(dl.alloc((size_t)total));
+  DYNA_TRY(launch_nw_edges_fill(nd, threshold, ro.p, di.p, dj.p, dm.p, dl.p, st));
+  DYNA_CUDA(cudaMemcpyAsync(i_out, di.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaMemcpyAsync(j_out, dj.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaMemcpyAsync(matches_out, dm.p, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaMemcpyAsync(length_out, dl.p, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
   return DYNA_OK;
 }

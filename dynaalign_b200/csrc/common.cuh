@@ -129,4 +129,8 @@ inline int64_t tri_diag_rows(int64_t n, int64_t r) { return r * n - r * (r - 1) 
 
 constexpr int kNumSMsB200 = 148;
 
+// exclusive scan of per-row counts (one block; rows <= a few hundred thousand) + grand total; defined in mh_kernels.cu
+int launch_scan_rows(const unsigned long long* d_in, unsigned long long* d_out, int64_t rows, unsigned long long* d_total,
+                     cudaStream_t st);
+
 }  // namespace dyna

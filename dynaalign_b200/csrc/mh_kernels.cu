@@ -969,7 +969,12 @@ int launch_mh_edges_count(const uint16_t* d_counts, int64_t n, int64_t row_begin
   mh_edges_kernel<false><<<grid, 256, 0, st>>>(d_counts, n, row_begin, row_end, tri_strict_rows(n, row_begin), min_count,
                                                d_row_counts, nullptr, nullptr, nullptr, nullptr);
   DYNA_CUDA(cudaGetLastError());
-  mh_scan_rows_kernel<<<1, 1024, 0, st>>>(d_row_counts, d_row_offsets, rows, d_total);
+  return launch_scan_rows(d_row_counts, d_row_offsets, rows, d_total, st);
+}
+
+int launch_scan_rows(const unsigned long long* d_in, unsigned long long* d_out, int64_t rows, unsigned long long* d_total,
+                     cudaStream_t st) {
+  mh_scan_rows_kernel<<<1, 1024, 0, st>>>(d_in, d_out, rows, d_total);
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }

@@ -206,6 +206,23 @@ DYNA_API int dyna_nw_plan_fetch(dyna_nw_plan*, uint32_t* matches_tri_out, uint32
 DYNA_API int dyna_nw_plan_fetch_packed8(dyna_nw_plan*, uint8_t* matches8_tri_out, uint8_t* length8_tri_out, void* stream);
 /* Same weighting as dyna_mh_plan_checksum over the NW triangle (diagonal included): sum_out[0] matches, [1] length. */
 DYNA_API int dyna_nw_plan_checksum(dyna_nw_plan*, uint64_t* sum_out /* 2 */, void* stream);
+/* Threshold + sparsify for sim_fn = similarityNW, the step right after the hot path in clusterbreak
+ * (R/clusterbreak.R:217-221: threshold <- quantile(sim[upper.tri(sim)], thresh_p); sim[sim < threshold] <- 0), without
+ * the dense matrix.  A recursion node is the subset `members[0..n_members)` of the plan's sequences (strictly
+ * increasing 0-based indices; NULL = all sequences): sim_fn(sub-cluster) (R/clusterbreak.R:250-254) is a sub-matrix of
+ * the root's, so nothing is re-aligned.  Results cover the node pairs whose row lies in the plan's row range; ranks add
+ * their histograms and concatenate their edge lists.
+ *   stat_histogram : hist_out[(matches) * (2*max_len+1) + length] over pairs a < b, (max_len+1) x (2*max_len+1) counters
+ *   quantile       : exact type-7 quantile of (double)matches/length; two empty sequences (NaN) -> R's quantile error
+ *   threshold_edges: pairs with matches > 0 and (double)matches/length >= threshold, row-major, node-local indices */
+DYNA_API int dyna_nw_plan_max_len(const dyna_nw_plan*); /* longest sequence of the plan (>= 1) */
+DYNA_API int dyna_nw_plan_stat_histogram(dyna_nw_plan*, const int32_t* members, int64_t n_members, uint64_t* hist_out, void* stream);
+DYNA_API int dyna_nw_plan_fetch_diagonal(dyna_nw_plan*, const int32_t* members, int64_t n_members, uint32_t* matches_out,
+                                uint32_t* length_out, void* stream); /* self-alignments = self-loop weights of netcluster */
+DYNA_API int dyna_quantile_type7_identities(const uint64_t* hist, int64_t mdim, int64_t ldim, double prob, double* threshold_out);
+DYNA_API int dyna_nw_plan_threshold_edges(dyna_nw_plan*, const int32_t* members, int64_t n_members, double threshold,
+                                 int64_t max_edges, int32_t* i_out, int32_t* j_out, uint32_t* matches_out,
+                                 uint32_t* length_out, int64_t* n_edges_out, void* stream);
 DYNA_API int64_t dyna_nw_plan_pairs(const dyna_nw_plan*);
 DYNA_API int64_t dyna_nw_plan_cells(const dyna_nw_plan*); /* sum of len_i*len_j over the plan's pairs */
 DYNA_API int dyna_nw_plan_launches(const dyna_nw_plan*);
