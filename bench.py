@@ -588,11 +588,76 @@ def phase_target_nw(ctx):
             sample_ok = sample_ok and int(m8[slot]) == int(wm) and int(l8[slot]) == int(wl)
     del out_m, out_l
     ctx.release_memory()
+
+    # sparse e2e: what clusterbreak consumes at this size -- the exact type-7 quantile of the identities over ALL pairs
+    # and the edge list above it (R/clusterbreak.R:219-221 with sim_fn = similarityNW).  Host strings in, (matches, length)
+    # histogram + (i, j, matches, length) edges out.  thresh_p = 0.999: NW identities are almost never 0, so the
+    # reference's default 0.8 would keep a billion edges here; the top 0.1 % is ~5 M.
+    from dynaalign_b200.api import identities_at_least
+    offp = C.cast(pin_off.data_ptr(), C.POINTER(C.c_int64))
+    pins = [None] * 4
+    edge_cap = [0]
+    SP_P = 0.999
+
+    def sparse_step():
+        p = L.dyna_nw_plan_create(u8p(pin_res), offp, n, b"BLOSUM62", 10, 4, rb, re_, ctx.dev)
+        if not p:
+            raise RuntimeError(ctx._lib.last_error())
+        try:
+            ctx.check(L.dyna_nw_plan_run(p, ctx.st))
+            ml = L.dyna_nw_plan_max_len(p)
+            hist = np.zeros((ml + 1, 2 * ml + 1), dtype=np.uint64)
+            ctx.check(L.dyna_nw_plan_stat_histogram(p, None, 0, ptr(hist, C.c_uint64), ctx.st))
+            g = hist
+            if ctx.world > 1:  # the quantile is over all pairs: a few hundred counters summed across ranks (host logic)
+                t = torch.from_numpy(hist.astype(np.int64)).cuda()
+                ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.SUM)
+                g = np.ascontiguousarray(t.cpu().numpy().astype(np.uint64))
+            thr = C.c_double(0)
+            ctx.check(L.dyna_quantile_type7_identities(ptr(g, C.c_uint64), ml + 1, 2 * ml + 1, SP_P, C.byref(thr)))
+            cap = identities_at_least(hist, thr.value)
+            if pins[0] is None or cap > edge_cap[0]:
+                edge_cap[0] = cap
+                for q in range(4):
+                    pins[q] = torch.empty(max(cap, 1), dtype=torch.int32).pin_memory()
+            ne = C.c_int64(0)
+            ctx.check(L.dyna_nw_plan_threshold_edges(p, None, 0, thr.value, cap, C.cast(pins[0].data_ptr(), C.POINTER(C.c_int32)),
+                                                     C.cast(pins[1].data_ptr(), C.POINTER(C.c_int32)),
+                                                     C.cast(pins[2].data_ptr(), C.POINTER(C.c_uint32)),
+                                                     C.cast(pins[3].data_ptr(), C.POINTER(C.c_uint32)), C.byref(ne), ctx.st))
+        finally:
+            L.dyna_nw_plan_destroy(p)
+        return thr.value, ne.value, cap, identities_at_least(g, thr.value)
+
+    sparse_step()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        sp_thr, sp_ne, sp_cap, sp_all = sparse_step()
+    ctx.barrier()
+    sparse_s = ctx.max_over_ranks((time.perf_counter() - t0) / 2)
+    ctx.launches += 3 * (per_step + 4)
+    sp_total = ctx.sum_over_ranks(sp_ne)
+    sp_ok = all(ctx.gather(bool(sp_ne == sp_cap))) and sp_total == sp_all  # edge list == what the histogram says it must be
+    if ctx.rank == 0 and not ctx.args.skip_cpu and sp_ne > 0:  # and a sample of the edges against the oracle port
+        from oracle import port
+        rng = np.random.default_rng(6)
+        ei, ej, em, el = (pins[q].numpy()[:sp_ne] for q in range(4))
+        for q in rng.integers(0, sp_ne, size=200):
+            wm, wl = port.nw_pair(seqs[int(ei[q])], seqs[int(ej[q])])[:2]
+            sp_ok = sp_ok and int(em[q]) == int(wm) and int(el[q]) == int(wl) and wm / wl >= sp_thr and ei[q] < ej[q]
+    pins[:] = [None] * 4
+    ctx.release_memory()
     return {"n": n, "pairs": int(pairs), "cells": int(cells), "seconds": ms * 1e-3, "gcups": cells / (ms * 1e-3) / 1e9,
             "kernel": "nw_thread_rows2_kernel", "checksum": checksum,
             "e2e": {"seconds": e2e_s, "gcups": cells / e2e_s / 1e9, "d2h_bytes_per_step": int(2 * my_pairs),
                     "api": "dyna_nw_pair_stats8 per rank: validate + encode + plan + H2D + kernel + u8 pack + D2H of 2 bytes per pair "
                            "(matches, length <= 32), pinned host buffers"},
+            "e2e_sparse": {"seconds": sparse_s, "gcups": cells / sparse_s / 1e9, "thresh_p": SP_P, "threshold": sp_thr,
+                           "edges": int(sp_total), "d2h_bytes_per_step": int(16 * sp_ne), "edges_consistent": bool(sp_ok),
+                           "api": "dyna_nw_plan_create + run + stat_histogram + dyna_quantile_type7_identities + threshold_edges per rank: "
+                                  "clusterbreak's threshold step (R/clusterbreak.R:219-221) for sim_fn = similarityNW as an edge list, "
+                                  "host buffers in and out"},
             "oracle_sample_ok": sample_ok}
 
 
@@ -920,7 +985,21 @@ def small_configs(dev, with_cpu=False):
                     "third-party and not installed); signatures hashed once, sub-clusters gather them on the device"}
     except Exception as e:
         out["config3_clusterbreak_h3n2_1000"] = {"error": str(e)[:200]}
-    out["note"] = ("wall clock of the drop-in call (flatten + validate + H2D + kernels + expansion to the column-major double matrix "
+    # the same caller loop with sim_fn = similarityNW (config 2's similarity): aligned once, every recursion node read off
+    # the root's triangle on the device; the reference re-aligns each node (R/clusterbreak.R:217,250-254)
+    try:
+        spent = [0.0]
+        t0 = time.perf_counter()
+        res = da.clusterbreak(h3, timed_components, thresh_p=0.8, size_max=800, size_min=3, max_itr=50, verbose=False, sim="NW")
+        total = time.perf_counter() - t0
+        out["config2_clusterbreak_similarityNW_h3n2_1000"] = {
+            "seconds_total": total, "seconds_cluster_fn_host": spent[0], "seconds_similarity_threshold_edges": total - spent[0],
+            "recursion_nodes": res["calls"], "clustered": int(len(res["clustered_seq"])), "filtered": len(res["filtered_seq"]),
+            "note": "size_max=800 thresh_p=0.8 sim_fn=similarityNW(BLOSUM62, 10, 4); one NW triangle for all recursion nodes "
+                    "((matches, length) histogram -> exact type-7 quantile -> edge list per node on the device)"}
+    except Exception as e:
+        out["config2_clusterbreak_similarityNW_h3n2_1000"] = {"error": str(e)[:200]}
+    out["note"] =("wall clock of the drop-in call (flatten + validate + H2D + kernels + expansion to the column-major double matrix "
                    "+ D2H), best of 3; inputs are the reference's evp_peparray / h3n2sample extracts")
     return out
 

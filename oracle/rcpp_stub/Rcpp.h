@@ -6,7 +6,7 @@
 // It provides only the Rcpp surface those two files touch:
 //   Rcpp::stop / Rcpp::warning (printf-like, %s with std::string, %c, %d)
 //   CharacterVector: (n) ctor, length(), operator[] (read as string, assign string)
-//   NumericMatrix:   (r,c) ctor zero-filled column-major, operator()(i,j), attr("dimnames") = ..., attr(name) = double
+//   NumericMatrix:   (r,c) ctor zero-filled column-major, operator()(i,j), attr("dimnames") = ..., attr(name) = double / std::vector<double>
 //   List::create(a, b), as<std::string>(elem)
 //   IntegerVector / NumericVector / IntegerMatrix (only what rpkg/src/dyna_shims.cpp needs, for the shim harness)
 // Nothing here mirrors Rcpp's implementation; it is a behavioural stub.
@@ -99,10 +99,12 @@ class NumericMatrix {
   std::vector<double> d_;
   List dimnames_;
   double scalar_attr_ = 0.0;
+  std::vector<double> vector_attr_;
   struct AttrProxy {
     NumericMatrix* m;
     AttrProxy& operator=(const List& l) { m->dimnames_ = l; return *this; }
     AttrProxy& operator=(double v) { m->scalar_attr_ = v; return *this; }  // the one scalar attribute the shims set
+    AttrProxy& operator=(const std::vector<double>& v) { m->vector_attr_ = v; return *this; }  // and the one vector attribute
   };
 public:
   NumericMatrix() : nr_(0), nc_(0) {}
@@ -116,6 +118,7 @@ public:
   double* begin() { return d_.data(); }
   const List& dimnames() const { return dimnames_; }
   double scalar_attr() const { return scalar_attr_; }
+  const std::vector<double>& vector_attr() const { return vector_attr_; }
 };
 
 // --- plain vectors / integer matrix (shim harness only) -------------------------

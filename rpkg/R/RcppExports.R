@@ -14,6 +14,12 @@ similarityNW <- function(sequences, matrixName = "BLOSUM62", gapOpen = 10L, gapE
 similarityMH_edges <- function(sequences, k = 4L, n_hash = 50L, thresh_p = 0.8)
     .Call(`_DynaAlign_similarityMH_edges`, sequences, k, n_hash, thresh_p)
 
+#' similarityNW + clusterbreak's quantile threshold, as an edge list (from, to, weight); attr "threshold", attr "self"
+#' (the self-alignment identities, i.e. the diagonal of the dense matrix)
+#' @export
+similarityNW_edges <- function(sequences, matrixName = "BLOSUM62", gapOpen = 10L, gapExt = 4L, thresh_p = 0.8)
+    .Call(`_DynaAlign_similarityNW_edges`, sequences, matrixName, gapOpen, gapExt, thresh_p)
+
 # internal: GPU halves of the pure-R MinHash pipeline (minhashGpu.R)
 .mh_signatures_linear <- function(ranks, offsets, a, b, m, n_hash)
     .Call(`_DynaAlign_mh_signatures_linear`, ranks, offsets, a, b, m, n_hash)

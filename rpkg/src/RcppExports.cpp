@@ -1,7 +1,7 @@
 // Routine registration for the DynaAlign shared object, hand-written (not compileAttributes output).
 // The first two entry points keep the reference's symbols and arities -- _DynaAlign_similarityMH/3 and
 // _DynaAlign_similarityNW/4 (its src/RcppExports.cpp:15,28,41-45) -- so `useDynLib(DynaAlign, .registration = TRUE)`
-// and the R stubs keep working unchanged.  Three more serve this package's own R code: the GPU halves of the pure-R
+// and the R stubs keep working unchanged.  Four more serve this package's own R code: the GPU halves of the pure-R
 // minhash() pipeline and the sparse threshold step of clusterbreak.
 #include <Rcpp.h>
 
@@ -17,6 +17,7 @@ using Rcpp::NumericVector;
 NumericMatrix similarityMH(CharacterVector sequences, int k, int n_hash);
 NumericMatrix similarityNW(CharacterVector sequences, std::string matrixName, int gapOpen, int gapExt);
 NumericMatrix similarityMH_edges(CharacterVector sequences, int k, int n_hash, double thresh_p);
+NumericMatrix similarityNW_edges(CharacterVector sequences, std::string matrixName, int gapOpen, int gapExt, double thresh_p);
 NumericMatrix mh_signatures_linear(IntegerVector ranks, NumericVector offsets, NumericVector a, NumericVector b, double m,
                                    int n_hash);
 NumericMatrix mh_distance_matrix(IntegerMatrix codes);
@@ -45,6 +46,13 @@ RcppExport SEXP _DynaAlign_similarityMH_edges(SEXP seqs, SEXP k, SEXP nHash, SEX
   END_RCPP
 }
 
+RcppExport SEXP _DynaAlign_similarityNW_edges(SEXP seqs, SEXP table, SEXP open, SEXP ext, SEXP p) {
+  BEGIN_RCPP
+  return Rcpp::wrap(similarityNW_edges(Rcpp::as<CharacterVector>(seqs), Rcpp::as<std::string>(table), Rcpp::as<int>(open),
+                                       Rcpp::as<int>(ext), Rcpp::as<double>(p)));
+  END_RCPP
+}
+
 RcppExport SEXP _DynaAlign_mh_signatures_linear(SEXP ranks, SEXP offsets, SEXP a, SEXP b, SEXP m, SEXP nHash) {
   BEGIN_RCPP
   return Rcpp::wrap(mh_signatures_linear(Rcpp::as<IntegerVector>(ranks), Rcpp::as<NumericVector>(offsets),
@@ -63,6 +71,7 @@ static const R_CallMethodDef kCallEntries[] = {
     {"_DynaAlign_similarityMH", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityMH), 3},
     {"_DynaAlign_similarityNW", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityNW), 4},
     {"_DynaAlign_similarityMH_edges", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityMH_edges), 4},
+    {"_DynaAlign_similarityNW_edges", reinterpret_cast<DL_FUNC>(&_DynaAlign_similarityNW_edges), 5},
     {"_DynaAlign_mh_signatures_linear", reinterpret_cast<DL_FUNC>(&_DynaAlign_mh_signatures_linear), 6},
     {"_DynaAlign_mh_distance_matrix", reinterpret_cast<DL_FUNC>(&_DynaAlign_mh_distance_matrix), 1},
     {nullptr, nullptr, 0}};

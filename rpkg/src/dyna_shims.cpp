@@ -132,6 +132,57 @@ NumericMatrix similarityMH_edges(CharacterVector sequences, int k = 4, int n_has
   return edges;
 }
 
+// similarityNW followed by the same threshold step: (edges x 3) matrix of (from, to, weight = matches / alignment length),
+// 1-based, row-major pair order; attr(, "threshold") is the quantile and attr(, "self") the n self-alignment identities
+// (the diagonal of the reference's matrix: the self-loop weights graph_from_adjacency_matrix(mode = "upper") would see).
+// [[Rcpp::export]]
+NumericMatrix similarityNW_edges(CharacterVector sequences, std::string matrixName = "BLOSUM62", int gapOpen = 10,
+                                 int gapExt = 4, double thresh_p = 0.8) {
+  const size_t n = sequences.length();
+  const Flat f = flatten(sequences);
+  dyna_nw_plan* plan = dyna_nw_plan_create(f.residues.data(), f.offsets.data(), static_cast<int64_t>(n), matrixName.c_str(),
+                                           gapOpen, gapExt, 0, static_cast<int64_t>(n), 0);
+  if (!plan) Rcpp::stop("%s", std::string(dyna_last_error()));
+  const size_t ml = static_cast<size_t>(dyna_nw_plan_max_len(plan));
+  const size_t mdim = ml + 1, ldim = 2 * ml + 1;
+  std::vector<uint64_t> hist(mdim * ldim, 0);
+  std::vector<int32_t> ei(1), ej(1);
+  std::vector<uint32_t> em(1), el(1), dm(n ? n : 1), dl(n ? n : 1);
+  double threshold = 0.0;
+  int64_t n_edges = 0;
+  int rc = dyna_nw_plan_run(plan, nullptr);
+  if (rc == DYNA_OK) rc = dyna_nw_plan_fetch_diagonal(plan, nullptr, 0, dm.data(), dl.data(), nullptr);
+  if (rc == DYNA_OK && n >= 2) {  // upper.tri of a 0 x 0 or 1 x 1 matrix is empty: no threshold, no edges
+    rc = dyna_nw_plan_stat_histogram(plan, nullptr, 0, hist.data(), nullptr);
+    if (rc == DYNA_OK) rc = dyna_quantile_type7_identities(hist.data(), static_cast<int64_t>(mdim), static_cast<int64_t>(ldim), thresh_p, &threshold);
+    if (rc == DYNA_OK) {
+      uint64_t cap = 0;
+      for (size_t m = 1; m < mdim; ++m)
+        for (size_t l = 1; l < ldim; ++l)
+          if (static_cast<double>(m) / static_cast<double>(l) >= threshold) cap += hist[m * ldim + l];
+      ei.resize(cap ? cap : 1);
+      ej.resize(cap ? cap : 1);
+      em.resize(cap ? cap : 1);
+      el.resize(cap ? cap : 1);
+      rc = dyna_nw_plan_threshold_edges(plan, nullptr, 0, threshold, static_cast<int64_t>(cap), ei.data(), ej.data(), em.data(),
+                                        el.data(), &n_edges, nullptr);
+    }
+  }
+  dyna_nw_plan_destroy(plan);  // released before any R error is raised
+  raise_on_error(rc);
+  NumericMatrix edges(static_cast<size_t>(n_edges), 3);
+  for (int64_t q = 0; q < n_edges; ++q) {
+    edges(q, 0) = ei[static_cast<size_t>(q)] + 1;
+    edges(q, 1) = ej[static_cast<size_t>(q)] + 1;
+    edges(q, 2) = static_cast<double>(em[static_cast<size_t>(q)]) / static_cast<double>(el[static_cast<size_t>(q)]);
+  }
+  std::vector<double> self(n);
+  for (size_t i = 0; i < n; ++i) self[i] = static_cast<double>(dm[i]) / static_cast<double>(dl[i]);  // NaN for an empty string
+  edges.attr("threshold") = threshold;
+  edges.attr("self") = self;
+  return edges;
+}
+
 // GPU half of compute_signature_matrix (R/minHash.R): returns the n_hash x n_docs double matrix, Inf where a
 // document has no shingle.
 // [[Rcpp::export]]

@@ -84,4 +84,20 @@ int shim_similarityMH_edges(const char* residues, const int64_t* offsets, int64_
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
+
+int shim_similarityNW_edges(const char* residues, const int64_t* offsets, int64_t n, const char* name, int go, int ge,
+                            double thresh_p, int64_t cap, double* edges_colmajor, int64_t* n_edges, double* threshold,
+                            double* self_out /* n */) {
+  try {
+    Rcpp::NumericMatrix m = similarityNW_edges(to_cv(residues, offsets, n), std::string(name), go, ge, thresh_p);
+    *n_edges = static_cast<int64_t>(m.nrow());
+    *threshold = m.scalar_attr();
+    if (static_cast<int64_t>(m.vector_attr().size()) != n) throw std::runtime_error("attr self has the wrong length");
+    for (int64_t i = 0; i < n; ++i) self_out[i] = m.vector_attr()[static_cast<size_t>(i)];
+    if (static_cast<int64_t>(m.nrow()) <= cap)
+      for (size_t c = 0; c < 3; ++c)
+        for (size_t r = 0; r < m.nrow(); ++r) edges_colmajor[c * static_cast<size_t>(cap) + r] = m(r, c);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
 }

@@ -139,3 +139,45 @@ def test_shim_similarityMH_edges_is_the_thresholded_reference_matrix(monkeypatch
         thr, edges = call_mh_edges(evp, 2, 50, p, n * n // 2)
         assert thr == want_thr
         assert (edges[:, 0] == wi + 1).all() and (edges[:, 1] == wj + 1).all() and (edges[:, 2] == dense[wi, wj]).all()
+
+
+def call_nw_edges(seqs, p, cap, name="BLOSUM62", go=10, ge=4):
+    res, off = flatten(seqs)
+    edges = np.zeros((max(cap, 1), 3), dtype=np.float64, order="F")
+    self_w = np.zeros(max(len(seqs), 1), dtype=np.float64)
+    ne, thr = C.c_int64(0), C.c_double(0)
+    rc = harness().shim_similarityNW_edges(res.ctypes.data_as(C.c_char_p), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           C.c_int64(len(seqs)), name.encode(), go, ge, C.c_double(p), C.c_int64(cap),
+                                           edges.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ne), C.byref(thr),
+                                           self_w.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc:
+        raise RuntimeError(harness().shim_last_error().decode())
+    return thr.value, edges[:ne.value], self_w[:len(seqs)]
+
+
+def test_shim_nw_edges_raise_reference_errors(golden):
+    e = golden["errors"]
+    for fn, key in [(lambda: call_nw_edges(["AA"], 0.8, 1, "BLOSUM63"), "nw_badname"), (lambda: call_nw_edges(["JA", "AA"], 0.8, 1), "nw_bad_seq1")]:
+        with pytest.raises(RuntimeError) as ei:
+            fn()
+        assert str(ei.value) == e[key]
+
+
+@pytest.mark.gpu
+def test_shim_similarityNW_edges_is_the_thresholded_reference_matrix(h3n2):
+    # R/clusterbreak.R:219-221 on the reference's own similarityNW matrix
+    from oracle.quantile_r import quantile_type7
+    seqs = h3n2[:40] + ["ARNDARND", "ARNDCRND", "WWWW"]
+    full = port.similarityNW(seqs)
+    n = len(seqs)
+    for p in (0.5, 0.93):
+        want_thr = quantile_type7(full[np.triu_indices(n, 1)], p)
+        dense = full.copy()
+        dense[dense < want_thr] = 0.0
+        wi, wj = np.nonzero(np.triu(dense, 1))
+        thr, edges, self_w = call_nw_edges(seqs, p, n * n // 2)
+        assert thr == want_thr
+        assert (edges[:, 0] == wi + 1).all() and (edges[:, 1] == wj + 1).all() and (edges[:, 2] == dense[wi, wj]).all()
+        assert (self_w == np.diag(full)).all()
+    thr, edges, self_w = call_nw_edges(["ARND"], 0.8, 4)  # 1 x 1: no pairs, no threshold, one self-loop
+    assert len(edges) == 0 and self_w[0] == 1.0

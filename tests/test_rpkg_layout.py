@@ -32,7 +32,7 @@ def test_namespace_is_a_superset_of_the_reference():
     mine = directives(os.path.join(RPKG, "NAMESPACE"))
     exports = {m.group(1) for d in mine for m in [re.match(r"export\((\w+)\)$", d)] if m}
     assert REF_EXPORTS <= exports
-    assert {"similarityMH_edges", "netcluster_edges"} <= exports
+    assert {"similarityMH_edges", "similarityNW_edges", "netcluster_edges"} <= exports
     assert "useDynLib(DynaAlign,.registration=TRUE)" in mine
     if os.path.exists(os.path.join(REF, "NAMESPACE")):
         ref = directives(os.path.join(REF, "NAMESPACE"))
