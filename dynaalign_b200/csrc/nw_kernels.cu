@@ -775,7 +775,13 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 // are zero-score padding below its last row and are never read back (each result is taken from its own last row).
 // Column j = i (the first row against itself) has no counterpart for row i+1; that half is computed and dropped.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRows2Threads = 512;
+#ifndef DYNA_ROWS2_THREADS
+#define DYNA_ROWS2_THREADS 512
+#endif
+#ifndef DYNA_ROWS2_LOOKAHEAD
+#define DYNA_ROWS2_LOOKAHEAD 2
+#endif
+constexpr int kRows2Threads = DYNA_ROWS2_THREADS;
 
 template <int R>
 struct Rec2 {
@@ -786,7 +792,9 @@ struct Rec2 {
   static constexpr int kStageBytes = (kRows2Threads / 32) * (kNwStageCols + 8);
   static constexpr int kTotal = kTableBytes + kStageBytes;
   __host__ __device__ static constexpr int first_needed(int q) { return (4 * q) / 3; }  // row of the quad's first word
-  __host__ __device__ static constexpr int load_row(int q) { return first_needed(q) >= 2 ? first_needed(q) - 2 : 0; }
+  __host__ __device__ static constexpr int load_row(int q) {
+    return first_needed(q) >= DYNA_ROWS2_LOOKAHEAD ? first_needed(q) - DYNA_ROWS2_LOOKAHEAD : 0;
+  }
 };
 
 template <int R>
@@ -937,10 +945,14 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
               } else {
                 strip_column4<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
               }
-              prevUpH = rH;
-              prevUpSA = rSA;
-              prevUpSB = rSB;
             }
+            // Unconditional: what the upper neighbour delivered in this step is the diagonal source of the next one.  A
+            // lane that has not started yet receives its neighbour's initial (= border) registers, which is exactly the
+            // diagonal of its first column; lane 0 starts at step 0 with the corner.  Outside the branch the two phases
+            // just alternate register names -- inside it these were three predicated moves per step.
+            prevUpH = rH;
+            prevUpSA = rSA;
+            prevUpSB = rSB;
           }
         }
       };

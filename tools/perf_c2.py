@@ -4,6 +4,9 @@ import ctypes as C, gzip, json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from dynaalign_b200 import _lib as _libmod
+if os.environ.get("DYNA_AB_LIB"):  # A/B against another build of the library (development only)
+    _libmod.LIB_PATH = os.environ["DYNA_AB_LIB"]
 from dynaalign_b200._lib import check, flatten, lib, ptr
 L = lib()
 with gzip.open(os.path.join(ROOT, "tests/golden/h3n2sample_first1000.json.gz"), "rt") as f:

@@ -5,6 +5,9 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dynaalign_b200 import synth
+from dynaalign_b200 import _lib as _libmod
+if os.environ.get("DYNA_AB_LIB"):  # A/B against another build of the library (development only)
+    _libmod.LIB_PATH = os.environ["DYNA_AB_LIB"]
 from dynaalign_b200._lib import check, flatten, lib, ptr
 L = lib()
 kind = "proteins"
