@@ -480,10 +480,20 @@ def phase_mh(ctx):
     edge_cap = [0]
     pins = [None, None, None]
 
-    def sparse_step(thresh_p=0.8):
+    j_inc, j_done = C.c_int64(0), C.c_int(0)
+
+    def match_all_pairs():
+        ctx.check(L.dyna_mh_plan_run_match(mplan, ctx.st))
+
+    def match_join():  # csrc/mh_sparse.cu: join on equal signature values; all-pairs if it declines
+        ctx.check(L.dyna_mh_plan_run_match_sparse(mplan, 0, C.byref(j_inc), C.byref(j_done), ctx.st))
+        if not j_done.value:
+            match_all_pairs()
+
+    def sparse_step(thresh_p=0.8, matcher=match_all_pairs):
         ctx.check(L.dyna_mh_plan_upload_sequences(mplan, u8p(pin_mres), moffp, k, ptr(seeds, C.c_uint32), ctx.st))
         msig.run(ctx.st)
-        ctx.check(L.dyna_mh_plan_run_match(mplan, ctx.st))
+        matcher()
         ctx.check(L.dyna_mh_plan_count_histogram(mplan, ptr(shist, C.c_uint64), ctx.st))
         g = shist
         if ctx.world > 1:  # the quantile is over all pairs: 501 counters summed across ranks (host logic, not a data-path collective)
@@ -515,6 +525,33 @@ def phase_mh(ctx):
     sp_edges_total = ctx.sum_over_ranks(sp_edges)
     ctx.launches += 4 * (3 + 1 + 3)
     table_mb = msig.table.numel() * 4 / 1e6 if msig.sharded else 0.0
+
+    # the join (single GPU: it needs every hash row sorted on this device, which the sharded relabelling does not leave)
+    join = None
+    if ctx.world == 1 and not msig.sharded:
+        def join_step():
+            msig.run(ctx.st)
+            match_join()
+
+        j_ms = ctx.timed_steps(join_step, 2, steps) / steps
+        if j_done.value:
+            jh = C.c_uint64(0)
+            ctx.check(L.dyna_mh_plan_checksum(mplan, C.byref(jh), ctx.st))
+            jhist = np.zeros(n_hash + 1, dtype=np.uint64)
+            ctx.check(L.dyna_mh_plan_count_histogram(mplan, ptr(jhist, C.c_uint64), ctx.st))
+            same = bool(int(jh.value) == checksum and (jhist == ghist).all())
+            sj = [sparse_step(0.8, match_join)]
+            t0 = time.perf_counter()
+            for _ in range(3):
+                sj.append(sparse_step(0.8, match_join))
+            torch.cuda.synchronize()
+            sj_s = (time.perf_counter() - t0) / 3
+            join = {"ms": j_ms, "pairs_s": total_pairs / (j_ms * 1e-3), "incidences": int(j_inc.value), "same_as_all_pairs": same,
+                    "sparse_s": sj_s, "sp_edges": int(sj[-1][1]), "sp_thr": sj[-1][0],
+                    "same_edges": bool(sj[-1] == (sp_thr, sp_edges))}
+            ctx.launches += (steps + 2) * 12 + 4 * 14
+        else:
+            join = {"declined": True, "incidences": int(j_inc.value)}
     L.dyna_mh_plan_destroy(mplan)
     ctx.release_memory()
     alg_bytes = MH_BYTES_PER_PAIR * total_pairs + 4.0 * mn * n_hash * ctx.world  # every rank reads all signatures once
@@ -523,7 +560,7 @@ def phase_mh(ctx):
             "dense8_s": dense8_s, "dense16_s": dense16_s, "n_esc": int(ctx.sum_over_ranks(n_esc.value)), "c8_ok": all(c8_ok),
             "sparse_s": sparse_s, "sp_thr": sp_thr, "sp_edges": sp_edges, "sp_edges_total": sp_edges_total,
             "h2d": int(mres.nbytes + moff.nbytes + seeds.nbytes), "sharded": msig.sharded, "table_mb": table_mb,
-            "alg_bytes": alg_bytes}
+            "alg_bytes": alg_bytes, "join": join}
 
 
 # ================================================================== NW on the 100,000 peptides (north_star target), all ranks
@@ -866,6 +903,7 @@ def main():
             "cpu_baseline": cpu,
             "minhash_pairs_per_sec": mh["pairs_s"],
             "minhash_e2e_pairs_per_sec": mh_total_pairs / mh["dense8_s"],
+            "minhash_join_pairs_per_sec": (mh["join"] or {}).get("pairs_s"),
             "minhash": {
                 "metric": "minhash_pairs_per_sec", "value": mh["pairs_s"], "unit": "pairs/s", "ms_per_step": mh["ms"],
                 "config": {"workload": "similarityMH k=4 n_hash=500 on synthetic %d peptides of 16 aa (BASELINE config 4), %d pairs per step; "
@@ -885,6 +923,17 @@ def main():
                                "edges": int(mh["sp_edges_total"]), "d2h_bytes_per_step": int(10 * mh["sp_edges"] + 8 * (n_hash + 1)),
                                "api": "upload_sequences + run_signatures + run_match + count_histogram + dyna_quantile_type7_counts + "
                                       "threshold_edges: clusterbreak's threshold step (R/clusterbreak.R:219-221) as an edge list, host buffers"},
+                "join": (None if mh["join"] is None else mh["join"] if "declined" in mh["join"] else {
+                    "value": mh["join"]["pairs_s"], "unit": "pairs/s", "ms_per_step": mh["join"]["ms"],
+                    "incidences": mh["join"]["incidences"], "same_checksum_and_histogram_as_all_pairs": mh["join"]["same_as_all_pairs"],
+                    "e2e_sparse": {"value": mh_total_pairs / mh["join"]["sparse_s"], "unit": "pairs/s", "thresh_p": 0.8,
+                                   "threshold": mh["join"]["sp_thr"], "edges": mh["join"]["sp_edges"],
+                                   "same_edges_as_all_pairs": mh["join"]["same_edges"]},
+                    "note": "same step as `value` (signatures + relabelling + match counts, device-timed) with the match counts "
+                            "computed by dyna_mh_plan_run_match_sparse: the hash rows are already sorted by the relabelling, every "
+                            "group of equal signature values emits its pairs, the pair list is radix-sorted (CUB) and run-length "
+                            "encoded.  Exact and data dependent: O(n * n_hash + matches) instead of O(n^2 * n_hash); `value` above stays "
+                            "the all-pairs kernel, whose rate does not depend on the data.  Single GPU (N > 1 shards the all-pairs kernel)"}),
                 "roofline": {"bound": "hbm", "achieved": mh["alg_bytes"] / world / (mh_match_ms * 1e-3) / 1e9,
                              "peak": peaks_hbm(), "unit": "GB/s",
                              "frac": mh["alg_bytes"] / world / (mh_match_ms * 1e-3) / 1e9 / peaks_hbm(),

@@ -68,6 +68,7 @@ _SIGS = {
     "dyna_quantile_type7_counts": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_double, _f64p, C.POINTER(C.c_int)]),
     "dyna_mh_plan_threshold_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _u16p, _i64p, C.c_void_p]),
     "dyna_mh_plan_run_match_fetch8": (C.c_int, [C.c_void_p, _u8p, C.c_int64, _i64p, _u16p, _i64p, C.c_void_p]),
+    "dyna_mh_plan_run_match_sparse": (C.c_int, [C.c_void_p, C.c_int64, _i64p, C.POINTER(C.c_int), C.c_void_p]),
     "dyna_mh_plan_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "dyna_mh_plan_pairs": (C.c_int64, [C.c_void_p]),
     "dyna_mh_plan_launches": (C.c_int, [C.c_void_p]),

@@ -200,41 +200,17 @@ def similarityNW_edges(sequences, matrixName="BLOSUM62", gapOpen=10, gapExt=4, t
         plan.close()
 
 
-def similarityMH_edges(sequences, k=4, n_hash=50, thresh_p=0.8, *, seed=None, seeds=None, device=0):
+def similarityMH_edges(sequences, k=4, n_hash=50, thresh_p=0.8, *, seed=None, seeds=None, device=0, join="auto"):
     """similarityMH followed by clusterbreak's thresholding (R/clusterbreak.R:217-221) without ever materialising the
     dense n x n matrix:  threshold <- quantile(sim[upper.tri(sim)], thresh_p);  sim[sim < threshold] <- 0.
-    Returns (threshold, i, j, weight) with 0-based i < j in row-major order and weight = count / n_hash."""
-    sequences = list(sequences)
-    n = len(sequences)
-    res, off = flatten(sequences)
-    if n == 0:
-        raise DynaAlignError(L.ERR_INVALID, "Input sequences vector cannot be empty")
-    if seeds is None:
-        seeds = hashfamily_seeds(lib().dyna_random_seed() if seed is None else seed, n_hash)
-    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
-    if k <= 0:
-        raise DynaAlignError(L.ERR_INVALID, "'k' must be a positive integer")
-    plan = lib().dyna_mh_plan_create(n, int(n_hash), 0, n, int(device))
-    if not plan:
-        raise DynaAlignError(L.ERR_CUDA, L.last_error())
+    Returns (threshold, i, j, weight) with 0-based i < j in row-major order and weight = count / n_hash.
+    join: "auto" (join on equal signature values when the data is sparse enough, else all-pairs), "never", "always"."""
+    plan = MinHashPlan(sequences, k, n_hash, seed=seed, seeds=seeds, device=device)
+    plan.join = join
     try:
-        check(lib().dyna_mh_plan_upload_sequences(plan, ptr(res, C.c_uint8), ptr(off, C.c_int64), int(k), ptr(seeds, C.c_uint32), None))
-        check(lib().dyna_mh_plan_run_signatures(plan, None))
-        check(lib().dyna_mh_plan_run_match(plan, None))
-        hist = np.zeros(n_hash + 1, dtype=np.uint64)
-        check(lib().dyna_mh_plan_count_histogram(plan, ptr(hist, C.c_uint64), None))
-        thr, mc = quantile_type7_counts(hist, n_hash, thresh_p)
-        cap = int(hist[max(mc, 1):].sum())
-        ei = np.zeros(max(cap, 1), dtype=np.int32)
-        ej = np.zeros(max(cap, 1), dtype=np.int32)
-        ec = np.zeros(max(cap, 1), dtype=np.uint16)
-        ne = C.c_int64(0)
-        check(lib().dyna_mh_plan_threshold_edges(plan, mc, cap, ptr(ei, C.c_int32), ptr(ej, C.c_int32), ptr(ec, C.c_uint16),
-                                                 C.byref(ne), None))
+        return plan.threshold_edges(thresh_p)
     finally:
-        lib().dyna_mh_plan_destroy(plan)
-    m = ne.value
-    return thr, ei[:m], ej[:m], ec[:m].astype(np.float64) / n_hash
+        plan.close()
 
 
 class MinHashPlan:
@@ -273,10 +249,32 @@ class MinHashPlan:
 
     __del__ = close
 
+    # "auto": try the join on equal signature values first (exact, O(n * n_hash + matches)); fall back to the all-pairs
+    # kernel when the data has too many matches for it to pay or the plan has no sorted rows.  "never" / "always" force one.
+    join = "auto"
+    joined = False       # the last match ran as a join
+    incidences = None    # (pair, hash function) matches the join counted, when it was consulted
+
+    def match_sparse(self, max_incidences=None):
+        """Run the join (dyna_mh_plan_run_match_sparse); returns True if it ran.  Default cap: the point where the
+        all-pairs kernel (~3e13 compares/s) is certainly faster than sorting the incidences."""
+        if max_incidences is None:
+            pairs = lib().dyna_mh_plan_pairs(self._h)
+            max_incidences = max(1 << 20, pairs * self.n_hash // 4000)
+        inc, done = C.c_int64(0), C.c_int(0)
+        check(lib().dyna_mh_plan_run_match_sparse(self._h, int(max_incidences), C.byref(inc), C.byref(done), None))
+        self.incidences = inc.value if inc.value >= 0 else None
+        if done.value:
+            self._matched, self.joined = True, True
+        return bool(done.value)
+
     def _match(self):
-        if not self._matched:
-            check(lib().dyna_mh_plan_run_match(self._h, None))
-            self._matched = True
+        if self._matched:
+            return
+        if self.join != "never" and self.match_sparse(None if self.join == "auto" else 0):
+            return
+        check(lib().dyna_mh_plan_run_match(self._h, None))
+        self._matched, self.joined = True, False
 
     def signatures(self):
         out = np.zeros((self.n, self.n_hash), dtype=np.uint32)
@@ -284,6 +282,7 @@ class MinHashPlan:
         return out
 
     def match_counts(self):
+        """The dense u16 triangle on the host (a join result is scattered into it on the device first)."""
         out = np.zeros(max(tri_strict_size(self.n), 1), dtype=np.uint16)
         if self._matched:
             check(lib().dyna_mh_plan_fetch_counts(self._h, ptr(out, C.c_uint16), None))
@@ -338,7 +337,9 @@ class MinHashPlan:
         h = lib().dyna_mh_plan_create_subset(self._h, ptr(idx, C.c_int64), len(idx), 0, len(idx))
         if not h:
             raise DynaAlignError(L.ERR_INVALID, L.last_error())
-        return MinHashPlan(n_hash=self.n_hash, _handle=h, _n=len(idx))
+        child = MinHashPlan(n_hash=self.n_hash, _handle=h, _n=len(idx))
+        child.join = self.join
+        return child
 
 
 class NWPlan:

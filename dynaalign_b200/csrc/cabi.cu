@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gather.cuh"
 #include "mh_kernels.cuh"
+#include "mh_sparse.cuh"
 #include "nw_kernels.cuh"
 #include "nw_post.cuh"
 
@@ -218,6 +219,16 @@ struct dyna_mh_plan {
   DevBuf<uint8_t> cub_temp;
   MhRelabelWork work;
   bool have_sequences = false, have_sig = false, have_sigT = false;
+  // The dense u16 triangle is allocated when a dense producer first needs it (a plan that only ever uses the sparse
+  // join below can describe inputs whose n(n-1)/2 counts would not fit any memory).
+  bool counts_valid = false;
+  // keys_out / vals_out hold EVERY hash row sorted by value (the relabelling ran over all code rows on this device)
+  bool sorted_rows = false;
+  // result of the sparse join (mh_sparse.cu): (pair key i*n+j, match count) for every pair of the row range with count >= 1
+  bool sparse_valid = false;
+  int64_t sp_runs = 0, sp_incidences = 0;
+  DevBuf<unsigned long long> sp_keys;
+  DevBuf<uint32_t> sp_counts;
   // Buffers are allocated and released through the stream-ordered allocator on the legacy default stream, while the
   // work runs on whatever stream the caller passes.  Every entry point records that stream here and nothing is
   // released (plan destruction, re-upload) before it has drained, so a released block can never still be in use --
@@ -277,8 +288,29 @@ int mh_plan_prepare_match_inputs(dyna_mh_plan* p, cudaStream_t st, int* launches
     if (code_row_end < 0) code_row_end = mh_hrows2(p->n_hash);
     DYNA_TRY(launch_mh_relabel(p->sigT.p, p->n, p->n_hash, p->npitch, p->hrows, p->work, code_row_begin, code_row_end, st, &lr));
     l += lr;
+    p->sorted_rows = code_row_begin == 0 && code_row_end == mh_hrows2(p->n_hash);
   }
+  p->counts_valid = p->sparse_valid = false;  // new signatures: earlier match results are stale
   if (launches) *launches = l;
+  return DYNA_OK;
+}
+
+int mh_plan_ensure_counts(dyna_mh_plan* p) {
+  if (p->counts.p) return DYNA_OK;
+  DYNA_TRY(check_device_fits(2.0 * (double)p->pairs, p->device, "the dense u16 match-count triangle"));
+  DYNA_TRY(p->counts.alloc((size_t)p->pairs));
+  DYNA_CUDA(cudaStreamSynchronize(0));  // stream-ordered on the legacy stream: visible to the caller's stream from here on
+  return DYNA_OK;
+}
+
+// the dense triangle for a consumer: already there, or scattered from the sparse join's runs
+int mh_plan_need_dense(dyna_mh_plan* p, cudaStream_t st, const char* who) {
+  if (p->counts_valid) return DYNA_OK;
+  if (!p->sparse_valid) return fail(DYNA_ERR_INVALID, "%s: no match counts on the device (run a match first)", who);
+  DYNA_TRY(mh_plan_ensure_counts(p));
+  DYNA_TRY(mh_sparse_densify(p->sp_keys.p, p->sp_counts.p, p->sp_runs, p->n, tri_strict_rows(p->n, p->row_begin), p->pairs,
+                             p->counts.p, st));
+  p->counts_valid = true;
   return DYNA_OK;
 }
 }  // namespace
@@ -298,8 +330,7 @@ extern "C" dyna_mh_plan* dyna_mh_plan_create(int64_t n, int n_hash, int64_t row_
   p->row_begin = row_begin;
   p->row_end = row_end;
   p->pairs = tri_strict_rows(n, row_end) - tri_strict_rows(n, row_begin);
-  if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch) || p->counts.alloc((size_t)p->pairs))
-    return nullptr;
+  if (p->sig.alloc((size_t)n * n_hash) || p->sigT.alloc((size_t)p->hrows * p->npitch)) return nullptr;
   if (mh_plan_setup16(p.get()) != DYNA_OK) return nullptr;
   // allocations are stream-ordered on the legacy default stream: make them visible to any stream the caller uses
   if (cudaStreamSynchronize(0) != cudaSuccess) {
@@ -392,9 +423,102 @@ extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
   int l = 0;
+  DYNA_TRY(mh_plan_ensure_counts(p));
   DYNA_TRY(launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, p->row_begin, p->row_end, p->counts.p,
                            p->use16 ? p->sigP.p : nullptr, p->use16 ? p->overflow.p : nullptr, st, &l));
   p->launches = l;
+  p->counts_valid = true;
+  p->sparse_valid = false;
+  return DYNA_OK;
+}
+
+// The same match counts by joining the sorted hash rows on equal signature values (mh_sparse.cu): work and memory
+// proportional to the number of (pair, hash function) matches instead of n^2 * n_hash.  *n_incidences_out = that number;
+// *done_out = 1 if the join ran (n_incidences <= max_incidences; 0 = the default cap from free device memory), 0 if the
+// caller should run the all-pairs kernel instead (too many matches, or the plan has no sorted rows: n < 2048 or a
+// sharded relabelling).  Afterwards count_histogram / threshold_edges / checksum read the join's result; fetch_counts
+// and counts_device_ptr scatter it into the dense triangle first.
+extern "C" int dyna_mh_plan_run_match_sparse(dyna_mh_plan* p, int64_t max_incidences, int64_t* n_incidences_out, int* done_out,
+                                             void* stream) {
+  if (!p || !done_out) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match_sparse: null argument");
+  *done_out = 0;
+  if (n_incidences_out) *n_incidences_out = -1;
+  if (!p->have_sigT) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_run_match_sparse: no signatures on the device");
+  if (!p->use16 || !p->sorted_rows) return DYNA_OK;
+  DYNA_TRY(use_device(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->last_stream = st;
+  p->launches = 0;
+  if (p->row_end <= p->row_begin || p->n < 2) {
+    p->sp_runs = p->sp_incidences = 0;
+    p->sparse_valid = true;
+    p->counts_valid = false;
+    *done_out = 1;
+    if (n_incidences_out) *n_incidences_out = 0;
+    return DYNA_OK;
+  }
+  DevBuf<unsigned long long> row_elems, row_pairs, row_eoff, row_poff, totals;
+  DYNA_TRY(row_elems.alloc((size_t)p->n_hash));
+  DYNA_TRY(row_pairs.alloc((size_t)p->n_hash));
+  DYNA_TRY(row_eoff.alloc((size_t)p->n_hash));
+  DYNA_TRY(row_poff.alloc((size_t)p->n_hash));
+  DYNA_TRY(totals.alloc(2));
+  DYNA_CUDA(cudaStreamSynchronize(0));
+  DYNA_TRY(mh_sparse_count_incidences(p->keys_out.p, p->n, p->n_hash, p->npitch, row_elems.p, row_pairs.p, row_eoff.p, row_poff.p,
+                                      totals.p, st));
+  unsigned long long tot[2] = {0, 0};
+  DYNA_CUDA(cudaMemcpyAsync(tot, totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  p->launches = 3;
+  const int64_t n_elems = (int64_t)tot[0], n_inc = (int64_t)tot[1];
+  if (n_incidences_out) *n_incidences_out = n_inc;
+  int64_t cap = max_incidences;
+  if (cap <= 0) {  // ~40 bytes per incidence across the emit / sort / encode buffers
+    size_t free_b = 0, total_b = 0;
+    cap = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ? (int64_t)(free_b / 64) : (1ll << 27);
+  }
+  cap = std::min<int64_t>(cap, (1ll << 31) - 2);
+  if (n_inc > cap) return DYNA_OK;  // dense data: the all-pairs kernel is the right tool
+  if (n_inc == 0) {
+    p->sp_runs = p->sp_incidences = 0;
+    p->sparse_valid = true;
+    p->counts_valid = false;
+    *done_out = 1;
+    return DYNA_OK;
+  }
+  DevBuf<uint32_t> el_pos, el_r;
+  DevBuf<unsigned long long> el_off, pair_keys, sorted, d_runs;
+  DevBuf<uint8_t> temp;
+  DYNA_TRY(el_pos.alloc((size_t)n_elems));
+  DYNA_TRY(el_r.alloc((size_t)n_elems));
+  DYNA_TRY(el_off.alloc((size_t)n_elems));
+  DYNA_TRY(pair_keys.alloc((size_t)n_inc));
+  DYNA_TRY(sorted.alloc((size_t)n_inc));
+  DYNA_TRY(d_runs.alloc(1));
+  const size_t tb = mh_sparse_sort_temp_bytes(n_inc, p->n);
+  DYNA_TRY(temp.alloc(tb));
+  if (p->sparse_valid) DYNA_CUDA(cudaStreamSynchronize(st));
+  p->sparse_valid = false;
+  DYNA_TRY(p->sp_keys.alloc((size_t)n_inc));    // at most one run per incidence
+  DYNA_TRY(p->sp_counts.alloc((size_t)n_inc));
+  DYNA_CUDA(cudaStreamSynchronize(0));
+  DYNA_TRY(mh_sparse_emit(p->keys_out.p, p->vals_out.p, p->n, p->n_hash, p->npitch, row_eoff.p, row_poff.p, el_pos.p, el_r.p,
+                          el_off.p, n_elems, n_inc, p->row_begin, p->row_end, pair_keys.p, st));
+  DYNA_TRY(mh_sparse_sort_encode(pair_keys.p, sorted.p, n_inc, p->n, temp.p, tb, p->sp_keys.p, p->sp_counts.p, d_runs.p, st));
+  unsigned long long runs = 0, last_key = 0;
+  DYNA_CUDA(cudaMemcpyAsync(&runs, d_runs.p, sizeof runs, cudaMemcpyDeviceToHost, st));
+  DYNA_CUDA(cudaStreamSynchronize(st));
+  if (runs > 0) {
+    DYNA_CUDA(cudaMemcpyAsync(&last_key, p->sp_keys.p + (runs - 1), sizeof last_key, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaStreamSynchronize(st));
+    if (last_key == (unsigned long long)p->n * (unsigned long long)p->n) --runs;  // pairs of other ranks' rows
+  }
+  p->launches += 2 + 6;  // two of ours + the library's sort / encode passes
+  p->sp_runs = (int64_t)runs;
+  p->sp_incidences = n_inc;
+  p->sparse_valid = true;
+  p->counts_valid = false;
+  *done_out = 1;
   return DYNA_OK;
 }
 
@@ -413,6 +537,7 @@ extern "C" int dyna_mh_plan_fetch_counts(dyna_mh_plan* p, uint16_t* counts_out, 
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  DYNA_TRY(mh_plan_need_dense(p, st, "dyna_mh_plan_fetch_counts"));
   if (p->pairs > 0)
     DYNA_CUDA(cudaMemcpyAsync(counts_out, p->counts.p, sizeof(uint16_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
@@ -459,9 +584,16 @@ extern "C" int dyna_mh_plan_count_histogram(dyna_mh_plan* p, uint64_t* hist_out,
   p->last_stream = st;
   DevBuf<unsigned long long> d_hist;
   DYNA_TRY(d_hist.alloc((size_t)p->n_hash + 1));
-  DYNA_TRY(launch_mh_count_hist(p->counts.p, p->pairs, p->n_hash, d_hist.p, st));
+  const bool sparse = p->sparse_valid && !p->counts_valid;
+  if (sparse) {
+    DYNA_TRY(mh_sparse_histogram(p->sp_counts.p, p->sp_runs, p->n_hash, d_hist.p, st));
+  } else {
+    if (!p->counts_valid) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_count_histogram: no match counts on the device (run a match first)");
+    DYNA_TRY(launch_mh_count_hist(p->counts.p, p->pairs, p->n_hash, d_hist.p, st));
+  }
   DYNA_CUDA(cudaMemcpyAsync(hist_out, d_hist.p, sizeof(uint64_t) * (size_t)(p->n_hash + 1), cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
+  if (sparse) hist_out[0] = (uint64_t)(p->pairs - p->sp_runs);  // every pair without a run has no matching hash function
   return DYNA_OK;
 }
 
@@ -509,6 +641,38 @@ extern "C" int dyna_mh_plan_threshold_edges(dyna_mh_plan* p, int min_count, int6
   if (n_edges_out) *n_edges_out = 0;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
   const uint32_t mc = (uint32_t)std::max(min_count, 1);  // a zero count is never an edge (weight 0 in the adjacency matrix)
+  if (p->sparse_valid && !p->counts_valid) {  // the join's runs are already in row-major pair order: select and unpack
+    if (p->sp_runs == 0) return DYNA_OK;
+    DevBuf<uint32_t> sel;
+    DevBuf<unsigned long long> nsel;
+    DevBuf<uint8_t> temp;
+    const size_t tb = mh_sparse_select_temp_bytes(p->sp_runs);
+    DYNA_TRY(sel.alloc((size_t)p->sp_runs));
+    DYNA_TRY(nsel.alloc(1));
+    DYNA_TRY(temp.alloc(tb));
+    DYNA_CUDA(cudaStreamSynchronize(0));
+    DYNA_TRY(mh_sparse_select(p->sp_counts.p, p->sp_runs, mc, temp.p, tb, sel.p, nsel.p, st));
+    unsigned long long total = 0;
+    DYNA_CUDA(cudaMemcpyAsync(&total, nsel.p, sizeof total, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaStreamSynchronize(st));
+    if (n_edges_out) *n_edges_out = (int64_t)total;
+    if ((int64_t)total > max_edges)
+      return fail(DYNA_ERR_INVALID, "edge buffer too small: %lld edges, capacity %lld", (long long)total, (long long)max_edges);
+    if (total == 0) return DYNA_OK;
+    DevBuf<int32_t> di, dj;
+    DevBuf<uint16_t> dc;
+    DYNA_TRY(di.alloc((size_t)total));
+    DYNA_TRY(dj.alloc((size_t)total));
+    DYNA_TRY(dc.alloc((size_t)total));
+    DYNA_CUDA(cudaStreamSynchronize(0));
+    DYNA_TRY(mh_sparse_gather_edges(p->sp_keys.p, p->sp_counts.p, sel.p, (int64_t)total, p->n, di.p, dj.p, dc.p, st));
+    DYNA_CUDA(cudaMemcpyAsync(i_out, di.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaMemcpyAsync(j_out, dj.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaMemcpyAsync(count_out, dc.p, sizeof(uint16_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    DYNA_CUDA(cudaStreamSynchronize(st));
+    return DYNA_OK;
+  }
+  if (!p->counts_valid) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_threshold_edges: no match counts on the device (run a match first)");
   DevBuf<unsigned long long> rc, ro, tot;
   DYNA_TRY(rc.alloc((size_t)rows));
   DYNA_TRY(ro.alloc((size_t)rows));
@@ -545,6 +709,9 @@ extern "C" int dyna_mh_plan_run_match_fetch(dyna_mh_plan* p, uint16_t* counts_ou
   p->last_stream = st;
   const int64_t rows = p->row_end - p->row_begin;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
+  DYNA_TRY(mh_plan_ensure_counts(p));
+  p->counts_valid = true;  // every chunk below writes its part of the triangle
+  p->sparse_valid = false;
   const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, p->pairs / (64ll << 20)));
   // pair-balanced chunk boundaries inside [row_begin, row_end)
   std::vector<int64_t> b((size_t)nchunks + 1);
@@ -594,7 +761,12 @@ extern "C" int dyna_mh_plan_checksum(dyna_mh_plan* p, uint64_t* sum_out, void* s
   p->last_stream = st;
   DevBuf<unsigned long long> d_sum;
   DYNA_TRY(d_sum.alloc(1));
-  DYNA_TRY(launch_checksum_u16(p->counts.p, p->pairs, tri_strict_rows(p->n, p->row_begin), d_sum.p, st));
+  if (p->sparse_valid && !p->counts_valid) {
+    DYNA_TRY(mh_sparse_checksum(p->sp_keys.p, p->sp_counts.p, p->sp_runs, p->n, d_sum.p, st));
+  } else {
+    if (!p->counts_valid) return fail(DYNA_ERR_INVALID, "dyna_mh_plan_checksum: no match counts on the device (run a match first)");
+    DYNA_TRY(launch_checksum_u16(p->counts.p, p->pairs, tri_strict_rows(p->n, p->row_begin), d_sum.p, st));
+  }
   unsigned long long h = 0;
   DYNA_CUDA(cudaMemcpyAsync(&h, d_sum.p, sizeof h, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
@@ -618,6 +790,9 @@ extern "C" int dyna_mh_plan_run_match_fetch8(dyna_mh_plan* p, uint8_t* counts8_o
   if (n_esc_out) *n_esc_out = 0;
   const int64_t rows = p->row_end - p->row_begin;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
+  DYNA_TRY(mh_plan_ensure_counts(p));
+  p->counts_valid = true;  // every chunk below writes its part of the triangle
+  p->sparse_valid = false;
   const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, p->pairs / (64ll << 20)));
   std::vector<int64_t> b((size_t)nchunks + 1);
   b[0] = p->row_begin;
@@ -686,7 +861,11 @@ extern "C" int dyna_mh_plan_run_match_fetch8(dyna_mh_plan* p, uint8_t* counts8_o
 
 extern "C" int64_t dyna_mh_plan_pairs(const dyna_mh_plan* p) { return p ? p->pairs : 0; }
 extern "C" int dyna_mh_plan_launches(const dyna_mh_plan* p) { return p ? p->launches : 0; }
-extern "C" void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan* p) { return p ? p->counts.p : nullptr; }
+extern "C" void* dyna_mh_plan_counts_device_ptr(dyna_mh_plan* p) {
+  if (!p || use_device(p->device) != DYNA_OK || mh_plan_need_dense(p, p->last_stream, "dyna_mh_plan_counts_device_ptr") != DYNA_OK)
+    return nullptr;
+  return p->counts.p;
+}
 extern "C" void dyna_mh_plan_destroy(dyna_mh_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);

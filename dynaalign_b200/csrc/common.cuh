@@ -129,6 +129,12 @@ inline int64_t tri_diag_rows(int64_t n, int64_t r) { return r * n - r * (r - 1) 
 
 constexpr int kNumSMsB200 = 148;
 
+// weight of packed-triangle position k in the position-weighted checksums (gather.cu, mh_sparse.cu)
+__host__ __device__ inline unsigned long long checksum_weight(unsigned long long k) {
+  unsigned long long w = (k + 1ull) * 0x9E3779B97F4A7C15ull;
+  return w ^ (w >> 31);
+}
+
 // exclusive scan of per-row counts (one block; rows <= a few hundred thousand) + grand total; defined in mh_kernels.cu
 int launch_scan_rows(const unsigned long long* d_in, unsigned long long* d_out, int64_t rows, unsigned long long* d_total,
                      cudaStream_t st);

@@ -102,10 +102,7 @@ int launch_expand(const TriSlabs& s, const Value& v, int64_t n, int64_t c0, int6
 // ---- checksums: sum of value[k] * mix(global index) in wrap-around 64-bit arithmetic.  The weight depends on the
 // pair's GLOBAL position in the packed triangle, so the sum over all ranks' slabs equals the single-device sum only
 // if the slabs tile the triangle exactly (an off-by-one row in a partition changes it).
-__device__ __forceinline__ unsigned long long mix_index(unsigned long long k) {
-  unsigned long long w = (k + 1ull) * 0x9E3779B97F4A7C15ull;
-  return w ^ (w >> 31);
-}
+__device__ __forceinline__ unsigned long long mix_index(unsigned long long k) { return checksum_weight(k); }
 
 template <class T>
 __global__ void __launch_bounds__(256)

@@ -190,6 +190,17 @@ DYNA_API int dyna_mh_plan_run_match_fetch8(dyna_mh_plan*, uint8_t* counts8_out, 
 /* sum over the plan's slab of count[k] * w(global pair index k), w(k) = x ^ (x >> 31), x = (k+1)*0x9E3779B97F4A7C15,
  * in wrap-around 64-bit arithmetic.  Additive over the slabs of any row partition: summed over all ranks it equals
  * the single-device value exactly when the slabs tile the triangle (bench.py's multi-GPU parity check). */
+/* The same match counts by a JOIN on equal signature values instead of all-pairs compares (csrc/mh_sparse.cu): the hash
+ * rows are already sorted by the 16-bit relabelling; every group of equal values contributes its pairs, the pair list is
+ * sorted and run-length encoded.  Work and memory are O(n * n_hash + matches), not O(n^2 * n_hash) -- BASELINE config 4
+ * (2.5e12 compares) has ~6e6 matches -- and the plan needs no dense triangle, so n is not bound by n^2 memory.
+ * Exact, but data dependent: *n_incidences_out reports the number of (pair, hash function) matches and *done_out = 0
+ * means the join was NOT run (more than max_incidences matches; 0 = a cap derived from free device memory; or the plan
+ * has no sorted rows: n < 2048, or a sharded relabelling) and the caller should call dyna_mh_plan_run_match instead.
+ * After done = 1, count_histogram / threshold_edges / checksum read the join's result directly; fetch_counts and
+ * counts_device_ptr first scatter it into the dense u16 triangle. */
+DYNA_API int dyna_mh_plan_run_match_sparse(dyna_mh_plan*, int64_t max_incidences, int64_t* n_incidences_out, int* done_out,
+                                  void* stream);
 DYNA_API int dyna_mh_plan_checksum(dyna_mh_plan*, uint64_t* sum_out /* 1 */, void* stream);
 DYNA_API int64_t dyna_mh_plan_pairs(const dyna_mh_plan*);
 DYNA_API int dyna_mh_plan_launches(const dyna_mh_plan*); /* kernels enqueued by the last run_* call */

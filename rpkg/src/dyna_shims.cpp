@@ -4,6 +4,7 @@
 // happens here on R's main thread before/after the GPU call; the CUDA side never sees a SEXP.
 #include <Rcpp.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <limits>
@@ -107,7 +108,15 @@ NumericMatrix similarityMH_edges(CharacterVector sequences, int k = 4, int n_has
   int64_t n_edges = 0;
   int rc = dyna_mh_plan_upload_sequences(plan, f.residues.data(), f.offsets.data(), k, seeds.data(), nullptr);
   if (rc == DYNA_OK) rc = dyna_mh_plan_run_signatures(plan, nullptr);
-  if (rc == DYNA_OK) rc = dyna_mh_plan_run_match(plan, nullptr);
+  // match counts: the join on equal signature values when the data is sparse enough for it (exact either way; the cap is
+  // where the all-pairs kernel is certainly faster), otherwise the all-pairs kernel
+  int joined = 0;
+  if (rc == DYNA_OK) {
+    const int64_t pairs = dyna_mh_plan_pairs(plan);
+    int64_t incidences = 0;
+    rc = dyna_mh_plan_run_match_sparse(plan, std::max<int64_t>(int64_t{1} << 20, pairs * n_hash / 4000), &incidences, &joined, nullptr);
+  }
+  if (rc == DYNA_OK && !joined) rc = dyna_mh_plan_run_match(plan, nullptr);
   if (rc == DYNA_OK) rc = dyna_mh_plan_count_histogram(plan, hist.data(), nullptr);
   int min_count = 0;
   if (rc == DYNA_OK) rc = dyna_quantile_type7_counts(hist.data(), n_hash, thresh_p, &threshold, &min_count);

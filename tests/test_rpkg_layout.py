@@ -77,7 +77,7 @@ def makevars_paths():
 
 def test_makevars_is_self_contained(tmp_path):
     paths = makevars_paths()
-    assert len(paths) == 14
+    assert len(paths) == 16
     for rel in paths:
         assert os.path.exists(os.path.join(RPKG, "src", rel)), rel
     # what `R CMD build` ships: links resolved into files; nothing may point outside the copy afterwards
