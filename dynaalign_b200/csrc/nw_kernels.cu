@@ -318,6 +318,21 @@ __device__ __forceinline__ uint32_t stat_select(uint32_t left, uint32_t up, uint
   return S;
 }
 
+// the same update with one select (ALU pipe) and one predicated add: one instruction less, one more on the ALU pipe.
+// nw_rows2_kernel is bound by issue slots with the ALU pipe at ~70 %, so a FEW rows per column can afford the trade
+// (rows chosen by the bit masks DYNA_ROWS2_SELMASK_A / _B).
+__device__ __forceinline__ uint32_t stat_select_sel(uint32_t left, uint32_t up, uint32_t dsum_a, uint32_t dsum_b, bool pu, bool pd) {
+  uint32_t S;
+  asm("{\n\t.reg .pred pu, pd;\n\t"
+      "setp.ne.u32 pu, %5, 0;\n\t"
+      "setp.ne.u32 pd, %6, 0;\n\t"
+      "selp.b32 %0, %2, %1, pu;\n\t"
+      "@pd add.u32 %0, %3, %4;\n\t}"
+      : "=&r"(S)
+      : "r"(left), "r"(up), "r"(dsum_a), "r"(dsum_b), "r"((uint32_t)pu), "r"((uint32_t)pd));
+  return S;
+}
+
 // Variants of the per-pair statistics update (same results):
 //   VAR 1: increments (1 | eq << 16) permuted out of the profile word (two PRMT per two cells); select by three adds
 //   VAR 2: increments read ready-made from a shared-memory table, 128 bits per four rows (strips R <= 12)
@@ -778,6 +793,12 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 #ifndef DYNA_ROWS2_THREADS
 #define DYNA_ROWS2_THREADS 512
 #endif
+#ifndef DYNA_ROWS2_SELMASK_A
+#define DYNA_ROWS2_SELMASK_A 0x7F
+#endif
+#ifndef DYNA_ROWS2_SELMASK_B
+#define DYNA_ROWS2_SELMASK_B 0
+#endif
 #ifndef DYNA_ROWS2_LOOKAHEAD
 #define DYNA_ROWS2_LOOKAHEAD 2
 #endif
@@ -846,8 +867,10 @@ __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t 
     bool puB, puA, pdB, pdA;
     const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);   // pred_hi -> pair 2 (row i+1), pred_lo -> pair 1 (row i)
     const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
-    const uint32_t SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
-    const uint32_t SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
+    const uint32_t SA = ((DYNA_ROWS2_SELMASK_A >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
+                                                 : stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = ((DYNA_ROWS2_SELMASK_B >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
+                                                     : stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
     diagH = Ho[k];
     dSA = SAo[k];
     dSB = SBo[k];
