@@ -893,6 +893,7 @@ struct dyna_nw_plan {
   int64_t n = 0, row_begin = 0, row_end = 0, pairs = 0, cells = 0;
   int gap_open = 0, gap_ext = 0;
   bool slant = false;
+  uint32_t bias16 = 0;  // offset of nw_rows2_kernel's unsigned 16-bit domain; 0 = signed lanes
   int launches = 0;
   int max_cols = 0;
   std::vector<std::unique_ptr<NwClass>> classes;
@@ -978,6 +979,14 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // for the flat -30000 sentinel below and the "- go" of a gap opening above.
   bool pack16 = p->slant && gap_ext >= 0 && gap_open >= 0 && (smin - 3ll * gap_open + 2ll * gap_ext) >= -24000;
   if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
+  // nw_rows2_kernel's unsigned domain: value + bias16 with bias16 = -(lower bound) + go + margin, so that the smallest
+  // value still exceeds go (H - go never wraps) and 0 is "minus infinity"; the largest is 32000 + bias16 < 65536 because
+  // the lower bound is above -24000.  Needs every table score + 2*ge to be non-negative (the diagonal step is then a plain
+  // add that cannot borrow from the upper half).  DYNA_NW_U16=0 keeps the signed lanes (A/B measurements).
+  if (pack16 && smin + 2ll * gap_ext >= 0) {
+    p->bias16 = (uint32_t)(-(smin - 3ll * gap_open + 2ll * gap_ext) + gap_open + 64);
+    if (const char* e = getenv("DYNA_NW_U16")) if (atoi(e) == 0) p->bias16 = 0;
+  }
   // rows above this length take the multi-pass form of the packed kernel (strips of <= 12 rows keep the fast
   // ping-pong / increment-table configuration); measured cross-over against the single-pass tall-strip form
   int mp_min_rows = 32 * kNwWarp2MaxR + 1;  // 385..640 rows: single pass with tall strips measured faster (2.60 vs 2.25 TCUPS)
@@ -1197,6 +1206,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
   d.gap_ext = p->gap_ext;
   d.one = 1u;
   d.zero = 0u;
+  d.bias16 = p->bias16;
   p->launches = 0;
   p->last_stream = st;
   const bool fork = p->side[0] != nullptr;

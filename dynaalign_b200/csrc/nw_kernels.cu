@@ -793,6 +793,12 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 #ifndef DYNA_ROWS2_THREADS
 #define DYNA_ROWS2_THREADS 512
 #endif
+#ifndef DYNA_TROWS2_SELMASK_A  // the same trade in nw_thread_rows2_kernel (short probes)
+#define DYNA_TROWS2_SELMASK_A 0xFFFF
+#endif
+#ifndef DYNA_TROWS2_SELMASK_B
+#define DYNA_TROWS2_SELMASK_B 0
+#endif
 #ifndef DYNA_ROWS2_SELMASK_A
 #define DYNA_ROWS2_SELMASK_A 0x7F
 #endif
@@ -844,7 +850,11 @@ __device__ __forceinline__ void build_records2(uint32_t* rec, const uint8_t* __r
   }
 }
 
-template <int R>
+// U (nw_rows2_kernel only): the UNSIGNED domain.  Every DP value is stored + d.bias16 so that it is a positive 16-bit
+// number, "minus infinity" is 0, and all table scores (s + 2*ge) are non-negative.  Then the diagonal step diagH + sP can
+// not carry between the halves and is a plain 32-bit add -- off the ALU pipe that the four remaining DPX instructions
+// and the selects share -- and the compares are the .U16x2 forms.  Same predicates, same statistics.
+template <int R, bool U = false>
 __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
                                               const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
                                               uint32_t (&SBn)[R], uint32_t rec_sh, uint32_t diagH, uint32_t dSA, uint32_t dSB,
@@ -863,10 +873,11 @@ __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t 
     }
     const uint32_t sP = w[3 * k], incA = w[3 * k + 1], incB = w[3 * k + 2];
     const uint32_t E = El[k];
-    const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    const uint32_t Mraw = U ? diagH + sP : __viaddmax_s16x2(diagH, sP, 0x80008000u);
     bool puB, puA, pdB, pdA;
-    const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);   // pred_hi -> pair 2 (row i+1), pred_lo -> pair 1 (row i)
-    const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    // pred_hi -> pair 2 (row i+1), pred_lo -> pair 1 (row i)
+    const uint32_t g = U ? __vibmax_u16x2(F, E, &puB, &puA) : __vibmax_s16x2(F, E, &puB, &puA);
+    const uint32_t H = U ? __vibmax_u16x2(Mraw, g, &pdB, &pdA) : __vibmax_s16x2(Mraw, g, &pdB, &pdA);
     const uint32_t SA = ((DYNA_ROWS2_SELMASK_A >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
                                                  : stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
     const uint32_t SB = ((DYNA_ROWS2_SELMASK_B >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
@@ -877,15 +888,15 @@ __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t 
     Hn[k] = H;
     SAn[k] = SA;
     SBn[k] = SB;
-    El[k] = __viaddmax_s16x2(H, ngo2, E);
-    F = __viaddmax_s16x2(H, ngo2, F);
+    El[k] = U ? __viaddmax_u16x2(H, ngo2, E) : __viaddmax_s16x2(H, ngo2, E);
+    F = U ? __viaddmax_u16x2(H, ngo2, F) : __viaddmax_s16x2(H, ngo2, F);
     upSA = SA;
     upSB = SB;
   }
   outF = F;
 }
 
-template <int R>
+template <int R, bool U>
 __global__ void __launch_bounds__(kRows2Threads, 1)
 nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   using RC = Rec2<R>;
@@ -900,8 +911,10 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   Stat2Consts c;
   c.one = d.one;
   c.zero = d.zero;
-  const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // register operand (see nw_thread2_kernel)
-  const uint32_t bord2 = pack16(ge - go);               // slanted border: -go + ge for every k >= 1
+  // register operands (see nw_thread2_kernel); U: everything + bias16, the sentinel is 0
+  const uint32_t sent2 = (U ? 0u : pack16(kSentinel16)) + c.zero;
+  const uint32_t bord2 = pack16(ge - go + (U ? (int)d.bias16 : 0));  // slanted border: -go + ge for every k >= 1
+  const uint32_t corner2 = U ? pack16((int)d.bias16) : 0u;
   const unsigned full = 0xFFFFFFFFu;
   const int src_lane = (lane + 31) & 31;  // rotating "shuffle up": lane 0 reads lane 31
   uint8_t* sC = stage_base + warp * (kNwStageCols + 8);
@@ -937,7 +950,7 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
         El[k] = sent2;
         SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
       }
-      uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
+      uint32_t prevUpH = (r0 == 0) ? corner2 : bord2;
       uint32_t prevUpSA = 0u, prevUpSB = 0u;
       uint32_t outF = sent2;
       const unsigned n_act = (lane <= lm) ? (unsigned)n : 0u;
@@ -964,9 +977,9 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
               const uint32_t cc = lds_u8(sC_sh + (uint32_t)jc);
               const uint32_t ra = rlane_sh + cc * (32u * RC::kStride * 4u);
               if (ph == 0) {
-                strip_column4<R>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+                strip_column4<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
               } else {
-                strip_column4<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+                strip_column4<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
               }
             }
             // Unconditional: what the upper neighbour delivered in this step is the diagonal source of the next one.  A
@@ -1925,8 +1938,10 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
     bool puB, puA, pdB, pdA;
     const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);
     const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
-    const uint32_t SA = stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
-    const uint32_t SB = stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
+    const uint32_t SA = ((DYNA_TROWS2_SELMASK_A >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
+                                                          : stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = ((DYNA_TROWS2_SELMASK_B >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
+                                                          : stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
     diagH = Ho[k];
     dSA = SAo[k];
     dSB = SBo[k];
@@ -2188,8 +2203,13 @@ int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 template <int R>
 int launch_rows2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   using RC = Rec2<R>;
-  DYNA_CUDA(cudaFuncSetAttribute(nw_rows2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, RC::kTotal));
-  nw_rows2_kernel<R><<<num_units, kRows2Threads, RC::kTotal, st>>>(d, d_units, num_units);
+  if (d.bias16 != 0u) {  // unsigned domain (host: every table score + 2*ge is non-negative, values + bias16 fit 16 bits)
+    DYNA_CUDA(cudaFuncSetAttribute(nw_rows2_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RC::kTotal));
+    nw_rows2_kernel<R, true><<<num_units, kRows2Threads, RC::kTotal, st>>>(d, d_units, num_units);
+  } else {
+    DYNA_CUDA(cudaFuncSetAttribute(nw_rows2_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RC::kTotal));
+    nw_rows2_kernel<R, false><<<num_units, kRows2Threads, RC::kTotal, st>>>(d, d_units, num_units);
+  }
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }

@@ -23,6 +23,7 @@ struct NwDeviceData {
   int gap_open, gap_ext;
   uint32_t one;          // always 1; passed as data so the compiler keeps it in a register (see strip_column)
   uint32_t zero;         // always 0; an opaque addend that lives in a uniform register / constant operand (see stat_select)
+  uint32_t bias16;       // nw_rows2_kernel: 0 = signed 16-bit lanes; otherwise the offset of its unsigned domain (strip_column4)
 };
 
 constexpr int kNwThreadMaxRows = 32;  // rows handled by the thread-per-pair kernel
