@@ -799,11 +799,23 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 #ifndef DYNA_TROWS2_SELMASK_B
 #define DYNA_TROWS2_SELMASK_B 0
 #endif
-#ifndef DYNA_ROWS2_SELMASK_A
+#ifndef DYNA_TROWS2_SELMASK_UA  // unsigned domain
+#define DYNA_TROWS2_SELMASK_UA 0xFFFF
+#endif
+#ifndef DYNA_TROWS2_SELMASK_UB
+#define DYNA_TROWS2_SELMASK_UB 0x0FFF
+#endif
+#ifndef DYNA_ROWS2_SELMASK_A  // signed lanes (five DPX instructions per row on the ALU pipe): 7 rows of the first pair
 #define DYNA_ROWS2_SELMASK_A 0x7F
 #endif
 #ifndef DYNA_ROWS2_SELMASK_B
 #define DYNA_ROWS2_SELMASK_B 0
+#endif
+#ifndef DYNA_ROWS2_SELMASK_UA  // unsigned domain (four DPX instructions per row): all rows of the first pair, 7 of the second
+#define DYNA_ROWS2_SELMASK_UA 0xFFF
+#endif
+#ifndef DYNA_ROWS2_SELMASK_UB
+#define DYNA_ROWS2_SELMASK_UB 0x7F
 #endif
 #ifndef DYNA_ROWS2_LOOKAHEAD
 #define DYNA_ROWS2_LOOKAHEAD 2
@@ -878,9 +890,9 @@ __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t 
     // pred_hi -> pair 2 (row i+1), pred_lo -> pair 1 (row i)
     const uint32_t g = U ? __vibmax_u16x2(F, E, &puB, &puA) : __vibmax_s16x2(F, E, &puB, &puA);
     const uint32_t H = U ? __vibmax_u16x2(Mraw, g, &pdB, &pdA) : __vibmax_s16x2(Mraw, g, &pdB, &pdA);
-    const uint32_t SA = ((DYNA_ROWS2_SELMASK_A >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
+    const uint32_t SA = (((U ? DYNA_ROWS2_SELMASK_UA : DYNA_ROWS2_SELMASK_A) >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
                                                  : stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
-    const uint32_t SB = ((DYNA_ROWS2_SELMASK_B >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
+    const uint32_t SB = (((U ? DYNA_ROWS2_SELMASK_UB : DYNA_ROWS2_SELMASK_B) >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
                                                      : stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
     diagH = Ho[k];
     dSA = SAo[k];
@@ -1548,7 +1560,7 @@ struct Rows2CoSmem {
   static constexpr int kTotal = kStageOff + kStageBytes + 2048;
 };
 
-template <int R, int K>
+template <int R, int K, bool U>
 __global__ void __launch_bounds__(kCoThreads, 1)
 nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   using RC = Rec2<R>;
@@ -1568,8 +1580,9 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   Stat2Consts c;
   c.one = d.one;
   c.zero = d.zero;
-  const uint32_t sent2 = pack16(kSentinel16) + c.zero;
-  const uint32_t bord2 = pack16(ge - go);
+  const uint32_t sent2 = (U ? 0u : pack16(kSentinel16)) + c.zero;     // U: the unsigned domain of strip_column4
+  const uint32_t bord2 = pack16(ge - go + (U ? (int)d.bias16 : 0));
+  const uint32_t corner2 = U ? pack16((int)d.bias16) : 0u;
   const unsigned full = 0xFFFFFFFFu;
   const int src_lane = (lane + 31) & 31;
   const bool producer = role < K - 1, consumer = role > 0;
@@ -1644,7 +1657,7 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
         El[k] = sent2;
         SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
       }
-      uint32_t prevUpH = (r0 == 0) ? 0u : bord2;
+      uint32_t prevUpH = (r0 == 0) ? corner2 : bord2;
       uint32_t prevUpSA = 0u, prevUpSB = 0u;
       uint32_t outF = sent2;
       const unsigned n_act = (lane <= lm) ? (unsigned)n : 0u;
@@ -1687,9 +1700,9 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
               const uint32_t cc = lds_u8(sC_sh + (uint32_t)jc);
               const uint32_t ra = rlane_sh + cc * (uint32_t)(L::kLanes * L::kStride * 4);
               if (ph == 0) {
-                strip_column4<R>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+                strip_column4<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
               } else {
-                strip_column4<R>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+                strip_column4<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
               }
               prevUpH = rH;
               prevUpSA = rSA;
@@ -1922,7 +1935,7 @@ nw_thread2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
 // pipe that kernel saturates (ncu r01d: ALU 78 %).
 // ------------------------------------------------------------------------------------------------
 // one column of the two-rows thread kernel: rows 0..R-1 of both row sequences against column residue class `base`
-template <int R>
+template <int R, bool U>
 __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
                                                     const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
                                                     uint32_t (&SBn)[R], uint32_t base, uint32_t diagH, uint32_t F, uint32_t ngo2,
@@ -1934,13 +1947,13 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
     const uint32_t incA = lds_u32(base + 12u * (unsigned)k + 4u);
     const uint32_t incB = lds_u32(base + 12u * (unsigned)k + 8u);
     const uint32_t E = El[k];
-    const uint32_t Mraw = __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    const uint32_t Mraw = U ? diagH + sP : __viaddmax_s16x2(diagH, sP, 0x80008000u);  // U: see strip_column4
     bool puB, puA, pdB, pdA;
-    const uint32_t g = __vibmax_s16x2(F, E, &puB, &puA);
-    const uint32_t H = __vibmax_s16x2(Mraw, g, &pdB, &pdA);
-    const uint32_t SA = ((DYNA_TROWS2_SELMASK_A >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
+    const uint32_t g = U ? __vibmax_u16x2(F, E, &puB, &puA) : __vibmax_s16x2(F, E, &puB, &puA);
+    const uint32_t H = U ? __vibmax_u16x2(Mraw, g, &pdB, &pdA) : __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    const uint32_t SA = (((U ? DYNA_TROWS2_SELMASK_UA : DYNA_TROWS2_SELMASK_A) >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
                                                           : stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
-    const uint32_t SB = ((DYNA_TROWS2_SELMASK_B >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
+    const uint32_t SB = (((U ? DYNA_TROWS2_SELMASK_UB : DYNA_TROWS2_SELMASK_B) >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
                                                           : stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
     diagH = Ho[k];
     dSA = SAo[k];
@@ -1948,14 +1961,14 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
     Hn[k] = H;
     SAn[k] = SA;
     SBn[k] = SB;
-    El[k] = __viaddmax_s16x2(H, ngo2, E);
-    F = __viaddmax_s16x2(H, ngo2, F);
+    El[k] = U ? __viaddmax_u16x2(H, ngo2, E) : __viaddmax_s16x2(H, ngo2, E);
+    F = U ? __viaddmax_u16x2(H, ngo2, F) : __viaddmax_s16x2(H, ngo2, F);
     upSA = SA;
     upSB = SB;
   }
 }
 
-template <int R>
+template <int R, bool U>
 __global__ void __launch_bounds__(kThreadThreads, R <= 16 ? 4 : 1)
 nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
   constexpr int TS = (3 * R) | 1;  // words per residue class (odd: conflict-free across classes)
@@ -1966,8 +1979,9 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
   Stat2Consts c;
   c.one = d.one;
   c.zero = d.zero;
-  const uint32_t sent2 = pack16(kSentinel16) + c.zero;  // register operand (see nw_thread2_kernel)
-  const uint32_t bord2 = pack16(ge - go);
+  const uint32_t sent2 = (U ? 0u : pack16(kSentinel16)) + c.zero;  // register operand (see nw_thread2_kernel)
+  const uint32_t bord2 = pack16(ge - go + (U ? (int)d.bias16 : 0));
+  const uint32_t corner2 = U ? pack16((int)d.bias16) : 0u;
   const uint32_t tab_sh = (uint32_t)__cvta_generic_to_shared(tab);
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -2006,15 +2020,15 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
         El[k] = sent2;
         SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
       }
-      uint32_t diag0 = 0u;  // corner (0,0); the border row (slanted: -go + ge) for every later column
+      uint32_t diag0 = corner2;  // corner (0,0); the border row (slanted: -go + ge) for every later column
       for (int t0 = 0; t0 < n; t0 += 2) {
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
           const int t = t0 + ph;
           if (t < n) {
             const uint32_t base = tab_sh + (uint32_t)b[t] * (uint32_t)(TS * 4);
-            if (ph == 0) thread_rows2_column<R>(H0, H1, El, SA0, SA1, SB0, SB1, base, diag0, sent2, ngo2, c);
-            else thread_rows2_column<R>(H1, H0, El, SA1, SA0, SB1, SB0, base, diag0, sent2, ngo2, c);
+            if (ph == 0) thread_rows2_column<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, base, diag0, sent2, ngo2, c);
+            else thread_rows2_column<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, base, diag0, sent2, ngo2, c);
             diag0 = bord2;
           }
         }
@@ -2231,8 +2245,13 @@ int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num
 template <int R>
 int launch_rows2co_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {
   using L = Rows2CoSmem<R, 2>;
-  DYNA_CUDA(cudaFuncSetAttribute(nw_rows2co_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-  nw_rows2co_kernel<R, 2><<<num_units, kCoThreads, L::kTotal, st>>>(d, d_units, num_units);
+  if (d.bias16 != 0u) {
+    DYNA_CUDA(cudaFuncSetAttribute(nw_rows2co_kernel<R, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    nw_rows2co_kernel<R, 2, true><<<num_units, kCoThreads, L::kTotal, st>>>(d, d_units, num_units);
+  } else {
+    DYNA_CUDA(cudaFuncSetAttribute(nw_rows2co_kernel<R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    nw_rows2co_kernel<R, 2, false><<<num_units, kCoThreads, L::kTotal, st>>>(d, d_units, num_units);
+  }
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
 }
@@ -2271,7 +2290,8 @@ int launch_nw_thread_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, 
   switch (R) {
 #define DYNA_CASE(RR)                                                                        \
   case RR:                                                                                   \
-    nw_thread_rows2_kernel<RR><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units); \
+    if (d.bias16 != 0u) nw_thread_rows2_kernel<RR, true><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units); \
+    else nw_thread_rows2_kernel<RR, false><<<num_units, kThreadThreads, 0, st>>>(d, d_units, num_units);               \
     break;
     DYNA_CASE(4) DYNA_CASE(8) DYNA_CASE(12) DYNA_CASE(16) DYNA_CASE(20) DYNA_CASE(24) DYNA_CASE(28) DYNA_CASE(32)
 #undef DYNA_CASE
