@@ -782,9 +782,10 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 //   * there is one staged column sequence, one residue load, one table address and one record stream per step;
 //   * the shorter-column padding (class 24, result capture at the shorter sequence's last column, pairing the columns
 //     by length) disappears: both alignments end in the same column, only in different rows.
-// Record per (class, lane): for each of the R strip rows three words -- packed scores, increment of pair 1 (1 | a1_k == c
-// << 16), increment of pair 2 -- read with 128-bit loads a few rows ahead of their use (stride 4*odd words: conflict-free
-// whatever class each lane reads).  3R words per lane and class is ~110 KB for R = 11, so a CTA owns a whole SM: 16
+// Record per (class, lane): for each of the R strip rows two words -- packed scores and the increment both pairs share
+// (Rec2 below; three words with one increment per pair until the statistics word was re-laid: 3826 -> see DESIGN.md) --
+// read with 128-bit loads a few rows ahead of their use (stride 4*odd words: conflict-free whatever class each lane
+// reads).  2R words per lane and class is ~86 KB for R = 11; with the staged sequences a CTA owns a whole SM: 16
 // warps, one unit = the two rows against up to 256 column sequences (16 per warp).
 // The two rows have different lengths m1, m2: the strip layout follows the longer one, the rows the shorter one lacks
 // are zero-score padding below its last row and are never read back (each result is taken from its own last row).
@@ -822,15 +823,31 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 #endif
 constexpr int kRows2Threads = DYNA_ROWS2_THREADS;
 
+// Statistics word of the two-rows kernels: bits 0..9 matches of pair 1 (row i), bits 10..19 matches of pair 2 (row i+1),
+// bits 20..31 diagonal steps.  With this layout ONE increment word per strip row and residue class,
+//     1 << 20 | (a2_k == c) << 10 | (a1_k == c),
+// serves both pairs: pair 1's statistics also count pair 2's matches along pair 1's path (and vice versa) in the field
+// they do not own, which is never read back.  A field grows by at most one per diagonal step and a path has at most
+// min(m, n) <= 768 of them, so no field carries into its neighbour.  Two words per row (scores, increment) instead of
+// three: the record stream -- the shared-memory pipe was at 85-90 % with three -- shrinks by a third.
+constexpr uint32_t kStat2DiagOne = 1u << 20;
+static_assert(kNwRows2CoMaxRows <= 1023 && 32 * 12 <= 1023 && kNwThreadMaxRows <= 1023, "10-bit match fields of the two-rows statistics word");
+__host__ __device__ __forceinline__ uint32_t inc2_word(bool eq1, bool eq2) {
+  return kStat2DiagOne | (eq2 ? 1u << 10 : 0u) | (eq1 ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t stat2_matches1(uint32_t s) { return s & 0x3FFu; }
+__device__ __forceinline__ uint32_t stat2_matches2(uint32_t s) { return (s >> 10) & 0x3FFu; }
+__device__ __forceinline__ uint32_t stat2_diag(uint32_t s) { return s >> 20; }
+
 template <int R>
 struct Rec2 {
-  static constexpr int kWords = 3 * R;
+  static constexpr int kWords = 2 * R;
   static constexpr int NQ = (kWords + 3) / 4;   // 128-bit loads per record
   static constexpr int kStride = (NQ | 1) * 4;  // words per lane record: a multiple of 4, an odd multiple
   static constexpr int kTableBytes = 24 * 32 * kStride * 4;
   static constexpr int kStageBytes = (kRows2Threads / 32) * (kNwStageCols + 8);
   static constexpr int kTotal = kTableBytes + kStageBytes;
-  __host__ __device__ static constexpr int first_needed(int q) { return (4 * q) / 3; }  // row of the quad's first word
+  __host__ __device__ static constexpr int first_needed(int q) { return 2 * q; }  // row of the quad's first word
   __host__ __device__ static constexpr int load_row(int q) {
     return first_needed(q) >= DYNA_ROWS2_LOOKAHEAD ? first_needed(q) - DYNA_ROWS2_LOOKAHEAD : 0;
   }
@@ -847,15 +864,13 @@ __device__ __forceinline__ void build_records2(uint32_t* rec, const uint8_t* __r
     const int ln = rem / RC::kStride, w = rem - ln * RC::kStride;
     uint32_t v = 0u;
     if (w < RC::kWords) {
-      const int k = w / 3, t = w - 3 * k, r = ln * R + k;
-      if (t == 0) {  // packed scores, sign-extended to 16 bits each; rows beyond a sequence's end score 0
+      const int k = w >> 1, r = ln * R + k;
+      if ((w & 1) == 0) {  // packed scores, sign-extended to 16 bits each; rows beyond a sequence's end score 0
         const int s1 = r < m1 ? (int)(int8_t)(sub[a1[r] * 24 + cls] + bias) : 0;
         const int s2 = r < m2 ? (int)(int8_t)(sub[a2[r] * 24 + cls] + bias) : 0;
         v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
-      } else if (t == 1) {
-        v = 1u | ((r < m1 && a1[r] == cls) ? 0x10000u : 0u);
       } else {
-        v = 1u | ((r < m2 && a2[r] == cls) ? 0x10000u : 0u);
+        v = inc2_word(r < m1 && a1[r] == cls, r < m2 && a2[r] == cls);
       }
     }
     rec[idx] = v;
@@ -883,7 +898,7 @@ __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t 
         w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
     }
-    const uint32_t sP = w[3 * k], incA = w[3 * k + 1], incB = w[3 * k + 2];
+    const uint32_t sP = w[2 * k], incA = w[2 * k + 1], incB = incA;
     const uint32_t E = El[k];
     const uint32_t Mraw = U ? diagH + sP : __viaddmax_s16x2(diagH, sP, 0x80008000u);
     bool puB, puA, pdB, pdA;
@@ -1016,11 +1031,11 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       }
       resA = __shfl_sync(full, resA, lmA);
       resB = __shfl_sync(full, resB, lmB);
-      if (lane == 0) {  // stat word: matches << 16 | diagonal steps;  length = m + n - diagonal steps
-        res_m1[pp] = resA >> 16;
-        res_l1[pp] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
-        res_m2[pp] = resB >> 16;
-        res_l2[pp] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+      if (lane == 0) {  // length = m + n - diagonal steps
+        res_m1[pp] = stat2_matches1(resA);
+        res_l1[pp] = (uint32_t)(m1 + n) - stat2_diag(resA);
+        res_m2[pp] = stat2_matches2(resB);
+        res_l2[pp] = (uint32_t)(m2 + n) - stat2_diag(resB);
       }
     }
     __syncthreads();
@@ -1539,9 +1554,9 @@ nw_warp2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
 // ------------------------------------------------------------------------------------------------
 // K5x2 cooperative + two rows: the cooperative wavefront of nw_warp2co_kernel (K warps, ring between neighbours) with
 // the operand layout of nw_rows2_kernel (rows i and i+1 in the two 16-bit halves, one column sequence, one record
-// stream, no score PRMT).  3R words per lane and class over 32*K lanes is 172 KB for R <= 9, K = 2 -- what fits next to
-// the rings and the staged sequences -- so it serves row pairs of 385..576 residues: the 566-residue HA sequences of
-// BASELINE config 2.  Rings: one per producer warp, one shared sink for the last warp of every group (its bottom row
+// stream, no score PRMT).  2R words per lane and class over 32*K lanes is 172 KB for R = 12, K = 2 -- it fits next to
+// the rings and the staged sequences -- so it serves row pairs of 385..768 residues, among them the 566-residue HA
+// sequences of BASELINE config 2 (with one increment word per pair, 3R words, the tables stopped at R = 9 = 576 rows).  Rings: one per producer warp, one shared sink for the last warp of every group (its bottom row
 // is never read), one constant border entry.
 // ------------------------------------------------------------------------------------------------
 template <int R, int K>
@@ -1616,15 +1631,13 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
         const int ln = rem / L::kStride, w = rem - ln * L::kStride;
         uint32_t v = 0u;
         if (w < RC::kWords) {
-          const int k = w / 3, t = w - 3 * k, r = ln * R + k;
-          if (t == 0) {
+          const int k = w >> 1, r = ln * R + k;
+          if ((w & 1) == 0) {
             const int s1 = r < m1 ? (int)(int8_t)(d.sub[a1[r] * 24 + cls] + 2 * ge) : 0;
             const int s2 = r < m2 ? (int)(int8_t)(d.sub[a2[r] * 24 + cls] + 2 * ge) : 0;
             v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
-          } else if (t == 1) {
-            v = 1u | ((r < m1 && a1[r] == cls) ? 0x10000u : 0u);
           } else {
-            v = 1u | ((r < m2 && a2[r] == cls) ? 0x10000u : 0u);
+            v = inc2_word(r < m1 && a1[r] == cls, r < m2 && a2[r] == cls);
           }
         }
         rec[idx] = v;
@@ -1730,12 +1743,12 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
         resB = __shfl_sync(full, resB, LmB & 31);
         if (lane == 0) {
           if (ownA) {
-            res_m1[pp] = resA >> 16;
-            res_l1[pp] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
+            res_m1[pp] = stat2_matches1(resA);
+            res_l1[pp] = (uint32_t)(m1 + n) - stat2_diag(resA);
           }
           if (ownB) {
-            res_m2[pp] = resB >> 16;
-            res_l2[pp] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+            res_m2[pp] = stat2_matches2(resB);
+            res_l2[pp] = (uint32_t)(m2 + n) - stat2_diag(resB);
           }
         }
       }
@@ -1928,10 +1941,10 @@ nw_thread2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
 // ------------------------------------------------------------------------------------------------
 // K4x2 "two rows": one thread per column sequence, the two 16-bit halves carry rows i and i+1 (both <= 32 residues) --
 // the short-probe counterpart of nw_rows2_kernel.  Every thread of the CTA aligns the same two row sequences, so the
-// table has no lane dimension: per residue class and strip row three words (packed scores, increment of pair 1,
-// increment of pair 2), class stride odd, so that the 32 lanes of a warp -- each at its own column residue -- read
+// table has no lane dimension: per residue class and strip row two words (packed scores, the increment both pairs
+// share: Rec2), class stride odd, so that the 32 lanes of a warp -- each at its own column residue -- read
 // conflict-free 32-bit words (equal classes broadcast).  Against nw_thread2_kernel (one row, two column sequences) a
-// row costs three shared loads instead of one load and three PRMT: 5 instead of 8 ALU-pipe instructions per row, the
+// row costs two shared loads instead of one load and three PRMT: 5 instead of 8 ALU-pipe instructions per row, the
 // pipe that kernel saturates (ncu r01d: ALU 78 %).
 // ------------------------------------------------------------------------------------------------
 // one column of the two-rows thread kernel: rows 0..R-1 of both row sequences against column residue class `base`
@@ -1943,9 +1956,8 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
   uint32_t dSA = 0u, dSB = 0u, upSA = 0u, upSB = 0u;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const uint32_t sP = lds_u32(base + 12u * (unsigned)k);
-    const uint32_t incA = lds_u32(base + 12u * (unsigned)k + 4u);
-    const uint32_t incB = lds_u32(base + 12u * (unsigned)k + 8u);
+    const uint32_t sP = lds_u32(base + 8u * (unsigned)k);
+    const uint32_t incA = lds_u32(base + 8u * (unsigned)k + 4u), incB = incA;  // one increment word for both pairs (Rec2)
     const uint32_t E = El[k];
     const uint32_t Mraw = U ? diagH + sP : __viaddmax_s16x2(diagH, sP, 0x80008000u);  // U: see strip_column4
     bool puB, puA, pdB, pdA;
@@ -1971,7 +1983,7 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
 template <int R, bool U>
 __global__ void __launch_bounds__(kThreadThreads, R <= 16 ? 4 : 1)
 nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units) {
-  constexpr int TS = (3 * R) | 1;  // words per residue class (odd: conflict-free across classes)
+  constexpr int TS = (2 * R) | 1;  // words per residue class (odd: conflict-free across classes)
   __shared__ uint32_t tab[24 * TS];
   const int tid = threadIdx.x;
   const int go = d.gap_open, ge = d.gap_ext;
@@ -1994,16 +2006,14 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
     for (int idx = tid; idx < 24 * TS; idx += kThreadThreads) {
       const int cls = idx / TS, w = idx - cls * TS;
       uint32_t v = 0u;
-      if (w < 3 * R) {
-        const int k = w / 3, t = w - 3 * k;
-        if (t == 0) {
+      if (w < 2 * R) {
+        const int k = w >> 1;
+        if ((w & 1) == 0) {
           const int s1 = k < m1 ? (int)(int8_t)(d.sub[a1[k] * 24 + cls] + 2 * ge) : 0;
           const int s2 = k < m2 ? (int)(int8_t)(d.sub[a2[k] * 24 + cls] + 2 * ge) : 0;
           v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
-        } else if (t == 1) {
-          v = 1u | ((k < m1 && a1[k] == cls) ? 0x10000u : 0u);
         } else {
-          v = 1u | ((k < m2 && a2[k] == cls) ? 0x10000u : 0u);
+          v = inc2_word(k < m1 && a1[k] == cls, k < m2 && a2[k] == cls);
         }
       }
       tab[idx] = v;
@@ -2041,12 +2051,12 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
         if (k == m2 - 1) resB = in1 ? SB1[k] : SB0[k];
       }
       const int64_t slot1 = pair_slot(d.n, row, j, d.slab_base);
-      d.matches[slot1] = resA >> 16;
-      d.length[slot1] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
+      d.matches[slot1] = stat2_matches1(resA);
+      d.length[slot1] = (uint32_t)(m1 + n) - stat2_diag(resA);
       if (j >= row2) {  // column `row` exists for the first row only
         const int64_t slot2 = pair_slot(d.n, row2, j, d.slab_base);
-        d.matches[slot2] = resB >> 16;
-        d.length[slot2] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+        d.matches[slot2] = stat2_matches2(resB);
+        d.length[slot2] = (uint32_t)(m2 + n) - stat2_diag(resB);
       }
     }
   }
@@ -2262,7 +2272,7 @@ int launch_nw_rows2co(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 #define DYNA_CASE(RR) \
   case RR:            \
     return launch_rows2co_R<RR>(d, d_units, num_units, st);
-    DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9)
+    DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9) DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12)
 #undef DYNA_CASE
     default:
       return fail(DYNA_ERR_UNSUPPORTED, "nw cooperative two-rows kernel: unsupported strip height %d", R);

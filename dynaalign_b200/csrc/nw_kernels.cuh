@@ -68,9 +68,8 @@ int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 // a unit is the row pair against up to kNwRows2UnitCols column sequences (units[].row is the first row)
 constexpr int kNwRows2UnitCols = 256;
 int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
-// cooperative two-rows kernel: row pairs of 385..576 residues (R = ceil(max/64) <= 9: what its tables allow in 227 KB);
-// units of up to kNwCoUnitCols columns
-constexpr int kNwRows2CoMaxRows = 64 * 9;
+// cooperative two-rows kernel: row pairs of 385..768 residues (R = ceil(max/64) <= 12); units of up to kNwCoUnitCols columns
+constexpr int kNwRows2CoMaxRows = 64 * 12;
 int launch_nw_rows2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 constexpr int kNwWarp2MpMaxRows = 32 * 12 * 8;  // 8 passes at most
 constexpr int kNwWarp2MpMaxCols = 2048;        // its column-sequence limit (staging buffer)
