@@ -804,7 +804,7 @@ nw_warp2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 #define DYNA_TROWS2_SELMASK_UA 0xFFFF
 #endif
 #ifndef DYNA_TROWS2_SELMASK_UB
-#define DYNA_TROWS2_SELMASK_UB 0x0FFF
+#define DYNA_TROWS2_SELMASK_UB 0x00FF
 #endif
 #ifndef DYNA_ROWS2_SELMASK_A  // signed lanes (five DPX instructions per row on the ALU pipe): 7 rows of the first pair
 #define DYNA_ROWS2_SELMASK_A 0x7F
@@ -1960,6 +1960,32 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
     const uint32_t incA = lds_u32(base + 8u * (unsigned)k + 4u), incB = incA;  // one increment word for both pairs (Rec2)
     const uint32_t E = El[k];
     const uint32_t Mraw = U ? diagH + sP : __viaddmax_s16x2(diagH, sP, 0x80008000u);  // U: see strip_column4
+    if (U && k == 0) {
+      // First row, unsigned domain: the vertical gap from the border row is "minus infinity" = 0, so max(F, E) = E, the
+      // "came from above" predicate can only hold where E is the sentinel too (column 0), and there the statistics above
+      // and to the left are both 0: the select has two cases, and F' = max(H - go, 0) is a plain subtraction (every real
+      // value exceeds go in both halves, see bias16 in cabi.cu).  Also keeps the compiler from expanding the DPX compare
+      // of a loop-invariant F into seven scalar instructions per column, which it did.
+      bool pdB, pdA;
+      const uint32_t H = __vibmax_u16x2(Mraw, E, &pdB, &pdA);
+      uint32_t SA, SB;
+      asm("{\n\t.reg .pred pd;\n\tsetp.ne.u32 pd, %3, 0;\n\tadd.u32 %0, %1, %4;\n\t@pd add.u32 %0, %2, %4;\n\t}"
+          : "=&r"(SA) : "r"(SAo[0]), "r"(incA), "r"((uint32_t)pdA), "r"(c.zero));
+      asm("{\n\t.reg .pred pd;\n\tsetp.ne.u32 pd, %3, 0;\n\tadd.u32 %0, %1, %4;\n\t@pd add.u32 %0, %2, %4;\n\t}"
+          : "=&r"(SB) : "r"(SBo[0]), "r"(incB), "r"((uint32_t)pdB), "r"(c.zero));
+      diagH = Ho[0];
+      dSA = SAo[0];
+      dSB = SBo[0];
+      Hn[0] = H;
+      SAn[0] = SA;
+      SBn[0] = SB;
+      El[0] = __viaddmax_u16x2(H, ngo2, E);
+      // per-half H - go (both halves exceed go): adding ngo2 = [-go : -go] carries once out of the low half, undone here
+      F = H + ngo2 - 0x10000u;
+      upSA = SA;
+      upSB = SB;
+      continue;
+    }
     bool puB, puA, pdB, pdA;
     const uint32_t g = U ? __vibmax_u16x2(F, E, &puB, &puA) : __vibmax_s16x2(F, E, &puB, &puA);
     const uint32_t H = U ? __vibmax_u16x2(Mraw, g, &pdB, &pdA) : __vibmax_s16x2(Mraw, g, &pdB, &pdA);
@@ -1994,7 +2020,8 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
   const uint32_t sent2 = (U ? 0u : pack16(kSentinel16)) + c.zero;  // register operand (see nw_thread2_kernel)
   const uint32_t bord2 = pack16(ge - go + (U ? (int)d.bias16 : 0));
   const uint32_t corner2 = U ? pack16((int)d.bias16) : 0u;
-  const uint32_t tab_sh = (uint32_t)__cvta_generic_to_shared(tab);
+  uint32_t tab_sh;  // opaque: otherwise the shared-window base is rebuilt (S2R + MOV + LEA) in every column
+  asm volatile("mov.u32 %0, %1;" : "=r"(tab_sh) : "r"((uint32_t)__cvta_generic_to_shared(tab)));
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
     const NwUnit un = units[u];
@@ -2031,12 +2058,16 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
         SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
       }
       uint32_t diag0 = corner2;  // corner (0,0); the border row (slanted: -go + ge) for every later column
-      for (int t0 = 0; t0 < n; t0 += 2) {
+      const uint8_t* bp = b;     // walked as a pointer: b[t] cost a 64-bit add (three ALU-pipe instructions) per column
+      for (int t0 = 0; t0 < n; t0 += 2, bp += 2) {
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
           const int t = t0 + ph;
           if (t < n) {
-            const uint32_t base = tab_sh + (uint32_t)b[t] * (uint32_t)(TS * 4);
+            uint32_t cres;
+            if (ph == 0) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cres) : "l"(bp));
+            else asm volatile("ld.global.nc.u8 %0, [%1+1];" : "=r"(cres) : "l"(bp));
+            const uint32_t base = tab_sh + cres * (uint32_t)(TS * 4);
             if (ph == 0) thread_rows2_column<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, base, diag0, sent2, ngo2, c);
             else thread_rows2_column<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, base, diag0, sent2, ngo2, c);
             diag0 = bord2;
