@@ -979,12 +979,13 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // for the flat -30000 sentinel below and the "- go" of a gap opening above.
   bool pack16 = p->slant && gap_ext >= 0 && gap_open >= 0 && (smin - 3ll * gap_open + 2ll * gap_ext) >= -24000;
   if (const char* e = getenv("DYNA_NW_PACK16")) pack16 = pack16 && (atoi(e) != 0);
-  // nw_rows2_kernel's unsigned domain: value + bias16 with bias16 = -(lower bound) + go + margin, so that the smallest
+  // The two-rows kernels' unsigned domain: value + bias16 with bias16 = -(lower bound) + go + margin, so that the smallest
   // value still exceeds go (H - go never wraps) and 0 is "minus infinity"; the largest is 32000 + bias16 < 65536 because
-  // the lower bound is above -24000.  Needs every table score + 2*ge to be non-negative (the diagonal step is then a plain
-  // add that cannot borrow from the upper half).  DYNA_NW_U16=0 keeps the signed lanes (A/B measurements).
-  if (pack16 && smin + 2ll * gap_ext >= 0) {
-    p->bias16 = (uint32_t)(-(smin - 3ll * gap_open + 2ll * gap_ext) + gap_open + 64);
+  // the lower bound is above -24000 (and go below 8000 with it).  Negative table scores are fine: the score words are
+  // integer sums of the two halves (score2_word in nw_kernels.cu).  DYNA_NW_U16=0 keeps the signed lanes (A/B measurements).
+  if (pack16) {
+    // (+ the most negative slanted score once more: the diagonal candidate diag + s is formed before the max)
+    p->bias16 = (uint32_t)(-(smin - 3ll * gap_open + 2ll * gap_ext) + gap_open + 64 + std::max<int64_t>(0, -(smin + 2ll * gap_ext)));
     if (const char* e = getenv("DYNA_NW_U16")) if (atoi(e) == 0) p->bias16 = 0;
   }
   // rows above this length take the multi-pass form of the packed kernel (strips of <= 12 rows keep the fast

@@ -853,7 +853,14 @@ struct Rec2 {
   }
 };
 
-template <int R>
+// U (unsigned domain, strip_column4): the score word is the INTEGER sum s2 * 65536 + s1, not the concatenation of two
+// 16-bit two's-complement halves -- the diagonal step is a plain 32-bit add there, and a negative s1 written as a
+// 16-bit half would carry into the upper half; as an integer sum the borrow is already in the word (equal for scores >= 0).
+__host__ __device__ __forceinline__ uint32_t score2_word(int s1, int s2, bool u) {
+  return u ? (uint32_t)(s2 * 65536 + s1) : (((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16));
+}
+
+template <int R, bool U>
 __device__ __forceinline__ void build_records2(uint32_t* rec, const uint8_t* __restrict__ a1, int m1,
                                                const uint8_t* __restrict__ a2, int m2, const int8_t* __restrict__ sub, int bias,
                                                int tid, int nthreads) {
@@ -868,7 +875,7 @@ __device__ __forceinline__ void build_records2(uint32_t* rec, const uint8_t* __r
       if ((w & 1) == 0) {  // packed scores, sign-extended to 16 bits each; rows beyond a sequence's end score 0
         const int s1 = r < m1 ? (int)(int8_t)(sub[a1[r] * 24 + cls] + bias) : 0;
         const int s2 = r < m2 ? (int)(int8_t)(sub[a2[r] * 24 + cls] + bias) : 0;
-        v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
+        v = score2_word(s1, s2, U);
       } else {
         v = inc2_word(r < m1 && a1[r] == cls, r < m2 && a2[r] == cls);
       }
@@ -877,10 +884,11 @@ __device__ __forceinline__ void build_records2(uint32_t* rec, const uint8_t* __r
   }
 }
 
-// U (nw_rows2_kernel only): the UNSIGNED domain.  Every DP value is stored + d.bias16 so that it is a positive 16-bit
-// number, "minus infinity" is 0, and all table scores (s + 2*ge) are non-negative.  Then the diagonal step diagH + sP can
-// not carry between the halves and is a plain 32-bit add -- off the ALU pipe that the four remaining DPX instructions
-// and the selects share -- and the compares are the .U16x2 forms.  Same predicates, same statistics.
+// U: the UNSIGNED domain.  Every DP value is stored + d.bias16 so that it is a positive 16-bit number and "minus
+// infinity" is 0.  The diagonal step diagH + sP is then a plain 32-bit add -- off the ALU pipe that the four remaining DPX
+// instructions and the selects share -- because both halves of the sum stay inside [0, 65535] (the table word is the
+// integer sum of the two scores, see score2_word: negative scores included), and the compares are the .U16x2 forms.
+// Same predicates, same statistics.
 template <int R, bool U = false>
 __device__ __forceinline__ void strip_column4(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
                                               const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
@@ -953,7 +961,7 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
     const int row = un.row, row2 = un.row + 1;
     const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
     __syncthreads();
-    build_records2<R>(rec, d.codes + d.off[row], m1, d.codes + d.off[row2], m2, d.sub, 2 * ge, tid, kRows2Threads);
+    build_records2<R, U>(rec, d.codes + d.off[row], m1, d.codes + d.off[row2], m2, d.sub, 2 * ge, tid, kRows2Threads);
     __syncthreads();
     const int lmA = (m1 - 1) / R, kmA = (m1 - 1) - lmA * R;
     const int lmB = (m2 - 1) / R, kmB = (m2 - 1) - lmB * R;
@@ -1635,7 +1643,7 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
           if ((w & 1) == 0) {
             const int s1 = r < m1 ? (int)(int8_t)(d.sub[a1[r] * 24 + cls] + 2 * ge) : 0;
             const int s2 = r < m2 ? (int)(int8_t)(d.sub[a2[r] * 24 + cls] + 2 * ge) : 0;
-            v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
+            v = score2_word(s1, s2, U);
           } else {
             v = inc2_word(r < m1 && a1[r] == cls, r < m2 && a2[r] == cls);
           }
@@ -1952,7 +1960,7 @@ template <int R, bool U>
 __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
                                                     const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
                                                     uint32_t (&SBn)[R], uint32_t base, uint32_t diagH, uint32_t F, uint32_t ngo2,
-                                                    const Stat2Consts& c) {
+                                                    uint32_t pgo2, const Stat2Consts& c) {
   uint32_t dSA = 0u, dSB = 0u, upSA = 0u, upSB = 0u;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
@@ -1980,8 +1988,7 @@ __device__ __forceinline__ void thread_rows2_column(const uint32_t (&Ho)[R], uin
       SAn[0] = SA;
       SBn[0] = SB;
       El[0] = __viaddmax_u16x2(H, ngo2, E);
-      // per-half H - go (both halves exceed go): adding ngo2 = [-go : -go] carries once out of the low half, undone here
-      F = H + ngo2 - 0x10000u;
+      F = H - pgo2;  // per-half H - go, pgo2 = [go : go]: no borrow, both halves exceed go
       upSA = SA;
       upSB = SB;
       continue;
@@ -2013,7 +2020,7 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
   __shared__ uint32_t tab[24 * TS];
   const int tid = threadIdx.x;
   const int go = d.gap_open, ge = d.gap_ext;
-  const uint32_t ngo2 = pack16(-go);
+  const uint32_t ngo2 = pack16(-go), pgo2 = pack16(go);
   Stat2Consts c;
   c.one = d.one;
   c.zero = d.zero;
@@ -2038,7 +2045,7 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
         if ((w & 1) == 0) {
           const int s1 = k < m1 ? (int)(int8_t)(d.sub[a1[k] * 24 + cls] + 2 * ge) : 0;
           const int s2 = k < m2 ? (int)(int8_t)(d.sub[a2[k] * 24 + cls] + 2 * ge) : 0;
-          v = ((uint32_t)s1 & 0xFFFFu) | ((uint32_t)s2 << 16);
+          v = score2_word(s1, s2, U);
         } else {
           v = inc2_word(k < m1 && a1[k] == cls, k < m2 && a2[k] == cls);
         }
@@ -2068,8 +2075,8 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
             if (ph == 0) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cres) : "l"(bp));
             else asm volatile("ld.global.nc.u8 %0, [%1+1];" : "=r"(cres) : "l"(bp));
             const uint32_t base = tab_sh + cres * (uint32_t)(TS * 4);
-            if (ph == 0) thread_rows2_column<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, base, diag0, sent2, ngo2, c);
-            else thread_rows2_column<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, base, diag0, sent2, ngo2, c);
+            if (ph == 0) thread_rows2_column<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, base, diag0, sent2, ngo2, pgo2, c);
+            else thread_rows2_column<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, base, diag0, sent2, ngo2, pgo2, c);
             diag0 = bord2;
           }
         }

@@ -21,7 +21,7 @@ ref = None
 for spec in (sys.argv[2:] or [""]):
     envs = dict(kv.split("=") for kv in spec.split(",") if kv)
     os.environ.update(envs)
-    p = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, 0, n, 0)
+    p = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", int(os.environ.get("PERF_GO", "10")), int(os.environ.get("PERF_GE", "4")), 0, n, 0)
     check(L.dyna_nw_plan_run(p, st)); torch.cuda.synchronize()
     ts = []
     for _ in range(3):
