@@ -1001,9 +1001,15 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // BASELINE config 5), but a small input needs the finer grain to fill 296 CTA slots (config 2: 2975 vs 2880 GCUPS)
   // rows of 33..384 residues are taken two at a time (rows i, i+1 against the same columns: nw_rows2_kernel);
   // DYNA_NW_ROWS2=0 restores one row against two column sequences (nw_warp2_kernel) for A/B measurements
-  // (its units are two rows x 256 columns on a whole SM: only for inputs large enough to fill the GPU with them)
-  bool use_rows2 = p->pairs >= (int64_t)kNwWarp2UnitColsMax * kNwMultiPassGrid * 32;
+  bool use_rows2 = p->pairs >= 10000;
   if (const char* e = getenv("DYNA_NW_ROWS2")) use_rows2 = atoi(e) != 0;
+  // its unit is the row pair against up to 256 column sequences on a whole SM; smaller inputs get narrower units so that
+  // there are ~9 or more per SM (measured on 330-residue proteins, GCUPS at 32 / 64 / 128 / 256 columns: n = 300
+  // 3608 / 3184 / 2411 / 2092, n = 600 3898 / 4002 / 3854 / 3197, n = 1000 3994 / 4084 / 4097 / 3938, n = 2000
+  // 4034 / 4157 / 4210 / 4228; the two-columns kernel it replaces there: 2619, 3066, 3179, 3248)
+  int rows2_cols = 32;
+  while (rows2_cols < kNwRows2UnitCols && p->pairs / (2 * 2 * rows2_cols) >= 1300) rows2_cols *= 2;
+  if (const char* e = getenv("DYNA_NW_ROWS2_COLS")) rows2_cols = std::min(kNwRows2UnitCols, std::max(1, atoi(e)));
   // short probes (rows <= 32 residues): two rows per thread; DYNA_NW_TROWS2=0 restores one row against two columns
   bool use_trows2 = pack16;
   if (const char* e = getenv("DYNA_NW_TROWS2")) use_trows2 = use_trows2 && atoi(e) != 0;
@@ -1110,8 +1116,8 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
         const int64_t nmax = range_max(i, n);
         if (fits16u(mx, nmax) && nmax <= kNwWarp2MaxCols) {
           NwClass* cls = get_class(8, nw_warp_R(mx));
-          for (int64_t j = i; j < n; j += kNwRows2UnitCols) {
-            const int64_t cnt = std::min<int64_t>(kNwRows2UnitCols, n - j);
+          for (int64_t j = i; j < n; j += rows2_cols) {
+            const int64_t cnt = std::min<int64_t>(rows2_cols, n - j);
             cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
             cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
           }
