@@ -1077,57 +1077,11 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   const bool force_warp2 = getenv("DYNA_NW_FORCE_WARP2") != nullptr;
   std::vector<int64_t> len_prefix((size_t)n + 1, 0);
   for (int64_t i = 0; i < n; ++i) len_prefix[(size_t)i + 1] = len_prefix[(size_t)i] + (offsets[i + 1] - offsets[i]);
-  for (int64_t i = row_begin; i < row_end; ++i) {
+  // one row against the column sequences [j_lo, j_hi): the kernel is chosen per unit from the unit's longest column
+  auto emit_single = [&](int64_t i, int64_t j_lo, int64_t j_hi) {
     const int m = (int)(offsets[i + 1] - offsets[i]);
-    if ((use_rows2 || use_rows2co || use_trows2) && !force_warp2 && i + 1 < row_end) {
-      // two-rows kernel: both rows in the single-pass packed range, similar length (the strip layout follows the longer
-      // one), and EVERY column sequence they meet within the 16-bit value range and the staging buffer
-      const int m2 = (int)(offsets[i + 2] - offsets[i + 1]);
-      const int mx = std::max(m, m2), mn = std::min(m, m2);
-      if (use_trows2 && mn >= 1 && mx <= kNwThreadMaxRows) {
-        // short probes: two rows per thread (nw_thread_rows2_kernel)
-        const int64_t nmax = range_max(i, n);
-        if (fits16u(mx, nmax)) {
-          NwClass* cls = get_class(10, nw_thread_R(mx));
-          for (int64_t j = i; j < n; j += 2 * kNwThreadUnitPairs) {
-            const int64_t cnt = std::min<int64_t>(2 * kNwThreadUnitPairs, n - j);
-            cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
-            cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
-          }
-          ++i;
-          continue;
-        }
-      }
-      if (use_rows2co && mn >= kNwCoMinRows && mx <= kNwRows2CoMaxRows && nw_co_R(mx) >= 7 && (mn - 1) / (32 * nw_co_R(mx)) == 1) {
-        // cooperative form: both rows reach into the second warp's block of 32*R rows
-        const int64_t nmax = range_max(i, n);
-        if (fits16u(mx, nmax) && nmax <= kNwWarp2MaxCols) {
-          NwClass* cls = get_class(9, nw_co_R(mx));
-          for (int64_t j = i; j < n; j += rows2co_cols) {
-            const int64_t cnt = std::min<int64_t>(rows2co_cols, n - j);
-            cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
-            cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
-          }
-          ++i;
-          continue;
-        }
-      }
-      if (use_rows2 && mn > kNwThreadMaxRows && mx <= 32 * 12 && 4 * mn >= 3 * mx) {
-        const int64_t nmax = range_max(i, n);
-        if (fits16u(mx, nmax) && nmax <= kNwWarp2MaxCols) {
-          NwClass* cls = get_class(8, nw_warp_R(mx));
-          for (int64_t j = i; j < n; j += rows2_cols) {
-            const int64_t cnt = std::min<int64_t>(rows2_cols, n - j);
-            cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
-            cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
-          }
-          ++i;  // row i+1 is covered
-          continue;
-        }
-      }
-    }
-    int64_t j = i;
-    while (j < n) {
+    int64_t j = j_lo;
+    while (j < j_hi) {
       int kind, R, step;
       const bool co_rows = use_co && !force_warp2 && m >= kNwCoMinRows && m <= kNwCoMaxRows;
       if (m == 0) { kind = 0; R = 0; step = 4096; }
@@ -1136,7 +1090,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
         const bool warp2_rows = m <= 32 * kNwWarp2MaxR && (m < mp_min_rows || force_warp2);
         const int pstep = nw_use_thread_kernel(m) && !force_warp2 ? 2 * kNwThreadUnitPairs
                           : co_rows ? kNwCoUnitCols : warp2_rows ? warp2_cols : 2 * kNwWarpUnitPairs;
-        const int64_t nmax = range_max(j, std::min<int64_t>(j + pstep, n));
+        const int64_t nmax = range_max(j, std::min<int64_t>(j + pstep, j_hi));
         const bool p16 = fits16u(m, nmax);
         if (force_warp2 && p16 && nmax <= kNwWarp2MaxCols && m <= 32 * kNwWarp2MaxR) { kind = 4; R = std::max(2, nw_warp_R(m)); step = pstep; }
         else if (nw_use_thread_kernel(m) && p16) { kind = 5; R = nw_thread_R(m); step = pstep; }
@@ -1153,11 +1107,69 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
       }
       // the multi-pass kernel keeps one scratch line per pair-set: at most 64 columns per unit
       if (kind == 6) step = std::min(step, 2 * kNwWarpUnitPairs);
-      const int64_t cnt = std::min<int64_t>(step, n - j);
+      const int64_t cnt = std::min<int64_t>(step, j_hi - j);
       NwClass* cls = get_class(kind, R);
       cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, (int32_t)cnt});
       cls->work += (int64_t)std::max(m, 1) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
       j += cnt;
+    }
+  };
+  // Two-rows kernels: row i takes a partner row i2 > i of the same kernel family and similar length -- the next such row
+  // within a window, not necessarily i + 1, so that inputs of mixed lengths pair up too.  Both rows then share the column
+  // sequences j >= i2; the columns i <= j < i2 exist for row i only (that half is computed and dropped: at most the
+  // window's width of them).  The decision is per UNIT: a unit whose longest column sequence leaves the 16-bit range or
+  // the staging buffer is handed to the single-row path for both rows, the other units of the pair keep the fast kernel.
+  // family: 1 short probes (nw_thread_rows2_kernel), 2 rows 33..384 (nw_rows2_kernel), 3 rows 385..768 (nw_rows2co_kernel)
+  auto family_of = [&](int m) -> int {
+    if (force_warp2) return 0;
+    if (use_trows2 && m >= 1 && m <= kNwThreadMaxRows) return 1;
+    if (use_rows2 && m > kNwThreadMaxRows && m <= 32 * 12) return 2;
+    if (use_rows2co && m >= kNwCoMinRows && m <= kNwRows2CoMaxRows && nw_co_R(m) >= 7) return 3;
+    return 0;
+  };
+  auto compatible = [&](int fam, int ma, int mb) -> bool {
+    const int mx = std::max(ma, mb), mn = std::min(ma, mb);
+    if (fam == 1) return true;
+    if (fam == 2) return 4 * mn >= 3 * mx;
+    // cooperative form: both rows reach into the second warp's block of 32*R rows
+    return nw_co_R(mx) >= 7 && (mn - 1) / (32 * nw_co_R(mx)) == 1;
+  };
+  int pair_window = 32;
+  if (const char* e = getenv("DYNA_NW_PAIR_WINDOW")) pair_window = std::min(4096, std::max(1, atoi(e)));
+  std::vector<uint8_t> covered((size_t)(row_end - row_begin), 0);
+  for (int64_t i = row_begin; i < row_end; ++i) {
+    if (covered[(size_t)(i - row_begin)]) continue;
+    const int m = (int)(offsets[i + 1] - offsets[i]);
+    const int fam = family_of(m);
+    int64_t i2 = -1;
+    if (fam != 0) {
+      for (int64_t q = i + 1; q < std::min<int64_t>(i + 1 + pair_window, row_end); ++q) {
+        if (covered[(size_t)(q - row_begin)]) continue;
+        const int mq = (int)(offsets[q + 1] - offsets[q]);
+        if (family_of(mq) == fam && compatible(fam, m, mq)) { i2 = q; break; }
+      }
+    }
+    if (i2 < 0) {
+      emit_single(i, i, n);
+      continue;
+    }
+    covered[(size_t)(i2 - row_begin)] = 1;
+    const int m2 = (int)(offsets[i2 + 1] - offsets[i2]);
+    const int mx = std::max(m, m2);
+    const int kind = fam == 1 ? 10 : fam == 2 ? 8 : 9;
+    const int R = fam == 1 ? nw_thread_R(mx) : fam == 2 ? nw_warp_R(mx) : nw_co_R(mx);
+    const int cols = fam == 1 ? 2 * kNwThreadUnitPairs : fam == 2 ? rows2_cols : rows2co_cols;
+    NwClass* cls = get_class(kind, R);
+    for (int64_t j = i; j < n; j += cols) {
+      const int64_t cnt = std::min<int64_t>(cols, n - j);
+      const int64_t nmax = range_max(j, j + cnt);
+      if (fits16u(mx, nmax) && (fam == 1 || nmax <= (fam == 2 ? kNwRows2MaxCols : nw_rows2co_max_cols(R)))) {
+        cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, nw_pack_count(cnt, i2 - i)});
+        cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
+      } else {
+        emit_single(i, j, j + cnt);
+        if (j + cnt > i2) emit_single(i2, std::max(j, i2), j + cnt);
+      }
     }
   }
 

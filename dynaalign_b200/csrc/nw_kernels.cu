@@ -300,6 +300,15 @@ constexpr int kSentinel16 = -30000;
 
 __device__ __forceinline__ uint32_t pack16(int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); }
 
+// A unit field read again where it is needed (opaque load) instead of being carried in a register across the step loop:
+// the two-rows kernels sit at the 128-register limit of 512-thread CTAs, and one more live value cost 6 % (measured when
+// NwUnit::row2 replaced "row + 1").
+__device__ __forceinline__ int reload_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 // stat update without touching the ALU pipe: S = left + cn; if (up) S = upS + cn; if (diag) S = diagS + inc,
 // written as one plain and two predicated 2-input adds (a SEL or a MOV would issue on the ALU pipe, which is the
 // pipe this kernel saturates; 2-input adds issue on the other integer pipes).  cn is the per-pair constant added on
@@ -845,7 +854,7 @@ struct Rec2 {
   static constexpr int NQ = (kWords + 3) / 4;   // 128-bit loads per record
   static constexpr int kStride = (NQ | 1) * 4;  // words per lane record: a multiple of 4, an odd multiple
   static constexpr int kTableBytes = 24 * 32 * kStride * 4;
-  static constexpr int kStageBytes = (kRows2Threads / 32) * (kNwStageCols + 8);
+  static constexpr int kStageBytes = (kRows2Threads / 32) * (kNwRows2MaxCols + 8);  // two records' words leave room for 2048 columns
   static constexpr int kTotal = kTableBytes + kStageBytes;
   __host__ __device__ static constexpr int first_needed(int q) { return 2 * q; }  // row of the quad's first word
   __host__ __device__ static constexpr int load_row(int q) {
@@ -952,16 +961,24 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
   const uint32_t corner2 = U ? pack16((int)d.bias16) : 0u;
   const unsigned full = 0xFFFFFFFFu;
   const int src_lane = (lane + 31) & 31;  // rotating "shuffle up": lane 0 reads lane 31
-  uint8_t* sC = stage_base + warp * (kNwStageCols + 8);
+  uint8_t* sC = stage_base + warp * (kNwRows2MaxCols + 8);
   const uint32_t sC_sh = (uint32_t)__cvta_generic_to_shared(sC);
   const uint32_t rlane_sh = (uint32_t)__cvta_generic_to_shared(rec + lane * RC::kStride);
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-    const NwUnit un = units[u];
-    const int row = un.row, row2 = un.row + 1;
-    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
+    NwUnit un = units[u];
+    const int row = un.row;
+    int m2;
+    const uint8_t* a2p;
+    {
+      const int row2 = row + (un.j_count >> 16);
+      un.j_count &= 0xFFFF;
+      m2 = d.off[row2 + 1] - d.off[row2];
+      a2p = d.codes + d.off[row2];
+    }
+    const int m1 = d.off[row + 1] - d.off[row];
     __syncthreads();
-    build_records2<R, U>(rec, d.codes + d.off[row], m1, d.codes + d.off[row2], m2, d.sub, 2 * ge, tid, kRows2Threads);
+    build_records2<R, U>(rec, d.codes + d.off[row], m1, a2p, m2, d.sub, 2 * ge, tid, kRows2Threads);
     __syncthreads();
     const int lmA = (m1 - 1) / R, kmA = (m1 - 1) - lmA * R;
     const int lmB = (m2 - 1) / R, kmB = (m2 - 1) - lmB * R;
@@ -1047,7 +1064,8 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
       }
     }
     __syncthreads();
-    {  // both rows' pairs occupy consecutive slots of the packed triangle; column `row` exists for the first row only
+    {  // both rows' pairs occupy consecutive slots of the packed triangle; the columns below row2 exist for the first row only
+      const int row2 = row + (reload_i32(&units[u].j_count) >> 16);
       const int64_t slot1 = pair_slot(d.n, row, un.j_begin, d.slab_base);
       const int skip = un.j_begin < row2 ? row2 - un.j_begin : 0;
       const int64_t slot2 = pair_slot(d.n, row2, un.j_begin + skip, d.slab_base) - skip;
@@ -1576,7 +1594,8 @@ struct Rows2CoSmem {
   static constexpr int kRings = kGroups * (K - 1) + 1;            // producers' rings + the sink
   static constexpr int kRingBytes = kRings * kCoRing * 16;
   static constexpr int kTableBytes = 24 * kLanes * kStride * 4;
-  static constexpr int kStageBytes = kWarps * (kNwStageCols + 8);
+  static constexpr int kStageCols = nw_rows2co_max_cols(R);       // 2048 where the tables leave room (R <= 10)
+  static constexpr int kStageBytes = kWarps * (kStageCols + 8);
   static constexpr int kRingOff = 0;                              // from the first 2048-byte aligned address
   static constexpr int kTableOff = kRingOff + kRingBytes;
   static constexpr int kStageOff = kTableOff + kTableBytes;
@@ -1609,7 +1628,7 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   const unsigned full = 0xFFFFFFFFu;
   const int src_lane = (lane + 31) & 31;
   const bool producer = role < K - 1, consumer = role > 0;
-  uint8_t* sC = stage_base + warp * (kNwStageCols + 8);
+  uint8_t* sC = stage_base + warp * (L::kStageCols + 8);
   const uint32_t sC_sh = (uint32_t)__cvta_generic_to_shared(sC);
   const uint32_t rlane_sh = (uint32_t)__cvta_generic_to_shared(rec + (role * 32 + lane) * L::kStride);
   // ring this warp writes: its own when another warp of the group consumes it, the shared sink otherwise
@@ -1624,15 +1643,17 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
   const uint32_t dn_cons_sh = (uint32_t)__cvta_generic_to_shared(&cons_cnt[producer ? warp + 1 : warp]);
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-    const NwUnit un = units[u];
-    const int row = un.row, row2 = un.row + 1;
-    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
+    NwUnit un = units[u];
+    const int row = un.row;
+    const int row2_top = row + (un.j_count >> 16);
+    un.j_count &= 0xFFFF;
+    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2_top + 1] - d.off[row2_top];
     __syncthreads();
     if (tid < L::kWarps) prod_cnt[tid] = cons_cnt[tid] = 0u;
     if (tid == 0) border_entry = make_uint4(bord2, sent2, 0u, 0u);
     {  // records of all 32*K lanes
       const uint8_t* __restrict__ a1 = d.codes + d.off[row];
-      const uint8_t* __restrict__ a2 = d.codes + d.off[row2];
+      const uint8_t* __restrict__ a2 = d.codes + d.off[row2_top];
       for (int idx = tid; idx < 24 * L::kLanes * L::kStride; idx += kCoThreads) {
         const int cls = idx / (L::kLanes * L::kStride);
         const int rem = idx - cls * (L::kLanes * L::kStride);
@@ -1763,6 +1784,7 @@ nw_rows2co_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_unit
     }
     __syncthreads();
     {
+      const int row2 = row + (reload_i32(&units[u].j_count) >> 16);
       const int64_t slot1 = pair_slot(d.n, row, un.j_begin, d.slab_base);
       const int skip = un.j_begin < row2 ? row2 - un.j_begin : 0;
       const int64_t slot2 = pair_slot(d.n, row2, un.j_begin + skip, d.slab_base) - skip;
@@ -2031,8 +2053,9 @@ nw_thread_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num
   asm volatile("mov.u32 %0, %1;" : "=r"(tab_sh) : "r"((uint32_t)__cvta_generic_to_shared(tab)));
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-    const NwUnit un = units[u];
-    const int row = un.row, row2 = un.row + 1;
+    NwUnit un = units[u];
+    const int row = un.row, row2 = un.row + (un.j_count >> 16);
+    un.j_count &= 0xFFFF;
     const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
     const uint8_t* __restrict__ a1 = d.codes + d.off[row];
     const uint8_t* __restrict__ a2 = d.codes + d.off[row2];

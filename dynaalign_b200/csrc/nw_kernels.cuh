@@ -9,8 +9,10 @@ namespace dyna {
 struct NwUnit {
   int32_t row;
   int32_t j_begin;
-  int32_t j_count;
+  int32_t j_count;  // two-rows kernels: column count in the low 16 bits, (second row - row) in the high 16 bits
 };
+// two-rows units: the second row sequence is row + delta, delta >= 1 (columns below it are computed for `row` alone)
+inline int32_t nw_pack_count(int64_t count, int64_t row_delta) { return (int32_t)(count | (row_delta << 16)); }
 
 struct NwDeviceData {
   const uint8_t* codes;  // residues encoded 0..23, all sequences back to back
@@ -67,9 +69,12 @@ int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 // two-rows packed kernel: rows i and i+1 (33..384 residues each, strips R <= 12) against the same column sequences;
 // a unit is the row pair against up to kNwRows2UnitCols column sequences (units[].row is the first row)
 constexpr int kNwRows2UnitCols = 256;
+constexpr int kNwRows2MaxCols = 2048;  // its column-sequence length limit (one staged sequence per warp)
 int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 // cooperative two-rows kernel: row pairs of 385..768 residues (R = ceil(max/64) <= 12); units of up to kNwCoUnitCols columns
 constexpr int kNwRows2CoMaxRows = 64 * 12;
+// its column-sequence length limit: the staging buffers share the SM's 227 KB with 172 KB of tables from R = 11 on
+constexpr int nw_rows2co_max_cols(int R) { return R <= 10 ? 2048 : 1024; }
 int launch_nw_rows2co(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
 constexpr int kNwWarp2MpMaxRows = 32 * 12 * 8;  // 8 passes at most
 constexpr int kNwWarp2MpMaxCols = 2048;        // its column-sequence limit (staging buffer)

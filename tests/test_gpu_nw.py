@@ -101,6 +101,24 @@ def test_two_rows_kernel(lo, hi):
         del os.environ["DYNA_NW_ROWS2"]
 
 
+@pytest.mark.parametrize("lo,hi", [(300, 384), (450, 640), (660, 768), (8, 32)])
+def test_two_rows_kernels_long_columns_and_mixed_lengths(lo, hi):
+    # the two-rows kernels stage column sequences of up to 2048 residues (1024 for the cooperative form from R = 11 on); a
+    # longer one sends only ITS unit of the row pair to the single-row kernels.  Rows pair with the next compatible row
+    # inside a window, not only with their neighbour: rows of other families are interleaved here.
+    rng = np.random.default_rng(lo + hi)
+    seqs = random_seqs(rng, 36, lo, hi, "ARNDCQEGHILKMFPSTWYV")
+    seqs += [random_seqs(rng, 1, L, L, "ARNDCQEGHILKMFPSTWYV")[0] for L in (1025, 1500, 2048, 2049, 2600)]
+    seqs += random_seqs(rng, 10, 1, 30) + random_seqs(rng, 8, 100, 200) + random_seqs(rng, 6, 400, 900) + [""]
+    rng.shuffle(seqs)
+    check_stats(seqs)
+    os.environ["DYNA_NW_PAIR_WINDOW"] = "1"  # neighbours only: same results
+    try:
+        check_stats(seqs[:40])
+    finally:
+        del os.environ["DYNA_NW_PAIR_WINDOW"]
+
+
 def test_cooperative_kernel_equals_single_warp_kernels():
     # same input through the cooperative kernel and (DYNA_NW_CO=0) the tall-strip / multi-pass kernels
     rng = np.random.default_rng(77)

@@ -14,7 +14,14 @@ kind = "proteins"
 if ":" in sys.argv[1]:
     kind, sys.argv[1] = sys.argv[1].split(":")
 n = int(sys.argv[1])
-seqs = synth.proteins_families(20000)[:n] if kind == "proteins" else synth.peptides_uniform(n, length=int(kind[3:] or 16))
+if kind == "proteins":
+    seqs = synth.proteins_families(20000)[:n]
+elif kind == "mix":  # proteome-like length mix: log-normal, median 300 residues, a few sequences beyond 1024
+    rng = np.random.default_rng(7)
+    lens = np.clip(rng.lognormal(np.log(300.0), 0.5, size=n), 30, 1800).astype(int)
+    seqs = [synth.RESIDUES20[rng.integers(0, 20, size=int(L))].tobytes() for L in lens]
+else:
+    seqs = synth.peptides_uniform(n, length=int(kind[3:] or 16))
 res, off = flatten(seqs)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 ref = None
