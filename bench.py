@@ -569,6 +569,60 @@ def phase_mh(ctx):
 
 
 # ================================================================== NW on the 100,000 peptides (north_star target), all ranks
+def phase_mixed_nw(ctx):
+    """NW on a proteome-like length mix (log-normal, median 300 residues, a few sequences beyond 1024): what the planner
+    makes of rows that do not sit next to a row of their own length.  Rank 0 only; device time and an oracle sample."""
+    if ctx.rank != 0:
+        return None
+    from dynaalign_b200._lib import flatten, ptr
+    from dynaalign_b200 import synth
+    L = ctx.L
+    rng = np.random.default_rng(7)
+    n = 3000
+    lens = np.clip(rng.lognormal(np.log(300.0), 0.5, size=n), 30, 1800).astype(int)
+    seqs = [synth.RESIDUES20[rng.integers(0, 20, size=int(x))].tobytes() for x in lens]
+    res, off = flatten(seqs)
+    plan = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, 0, n, ctx.dev)
+    if not plan:
+        raise RuntimeError(ctx._lib.last_error())
+    try:
+        cells = L.dyna_nw_plan_cells(plan)
+        st = ctx.st
+        ctx.check(L.dyna_nw_plan_run(plan, st))
+        ev = [ctx.torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(ctx.stream)
+        for _ in range(3):
+            ctx.check(L.dyna_nw_plan_run(plan, st))
+        ev[1].record(ctx.stream)
+        ctx.torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 3
+        launches = L.dyna_nw_plan_launches(plan)
+        ctx.launches += 4 * launches
+        pairs = L.dyna_nw_plan_pairs(plan)
+        mt, ln = np.zeros(pairs, dtype=np.uint32), np.zeros(pairs, dtype=np.uint32)
+        ctx.check(L.dyna_nw_plan_fetch(plan, ptr(mt, C.c_uint32), ptr(ln, C.c_uint32), None))
+        ctx.torch.cuda.synchronize()
+    finally:
+        L.dyna_nw_plan_destroy(plan)
+    ok = None
+    if not ctx.args.skip_cpu:
+        from oracle import port
+        ok = True
+        order = np.argsort(lens)
+        picks = [(int(order[-1 - k]), int(order[-40 - k])) for k in range(6)]            # long against long
+        picks += [(int(a), int(b)) for a, b in rng.integers(0, n, size=(150, 2))]
+        for a, b in picks:
+            i, j = min(a, b), max(a, b)
+            slot = i * n - i * (i - 1) // 2 + (j - i)
+            wm, wl = port.nw_pair(seqs[i], seqs[j])[:2]
+            ok = ok and int(mt[slot]) == int(wm) and int(ln[slot]) == int(wl)
+    ctx.release_memory()
+    return {"n": n, "length_min_median_max": [int(lens.min()), int(np.median(lens)), int(lens.max())], "cells": int(cells),
+            "seconds": ms * 1e-3, "gcups": cells / ms / 1e6, "kernel_launches_per_step": int(launches), "oracle_sample_ok": ok,
+            "note": "log-normal lengths (median 300, sigma 0.5, clipped to 30..1800), uniform residues, input order random: "
+                    "two-rows partner search in a 32-row window, kernel choice per unit, device time of dyna_nw_plan_run"}
+
+
 def phase_target_nw(ctx):
     """All pairs of the config-4 peptides through NW, row blocks over the ranks: device time, e2e in the 2-bytes-per-pair
     host form, checksums, and a sample of pairs against the oracle (rank 0)."""
@@ -761,6 +815,11 @@ def main():
     except Exception as e:  # never let a side measurement take the headline line down
         target = {"error": str(e)[:200]}
         ctx.release_memory()
+    try:
+        mixed = phase_mixed_nw(ctx)
+    except Exception as e:
+        mixed = {"error": str(e)[:200]}
+        ctx.release_memory()
 
     # ---------------- the R-facing call on all N GPUs of the box, from rank 0 (headline e2e)
     e2e_steps = max(1, min(args.steps, 3))
@@ -800,6 +859,7 @@ def main():
         other = small_configs(local_rank, with_cpu=(world == 1 and not args.skip_cpu))
         if other is not None:
             other["target_nw_100k_peptides"] = target
+            other["nw_mixed_lengths_3000"] = mixed
             other["similarityNW_inproc_n%d" % world] = {
                 "config5": {"n": n, "n_gpus": world, "seconds": inproc_s, "gcups": nw["total_cells"] / inproc_s / 1e9,
                             "d2h_bytes": 8 * n * n},
@@ -840,6 +900,7 @@ def main():
         "mh_narrow_form_lossless": mh["c8_ok"],
         "target_nw": cmp(key_tg, {"matches": target["checksum"][0], "length": target["checksum"][1]}) if "checksum" in target else None,
         "target_nw_oracle_sample": target.get("oracle_sample_ok"),
+        "nw_mixed_lengths_oracle_sample": (mixed or {}).get("oracle_sample_ok"),
         "nw_checksum": ["%016x" % c for c in nw["checksum"]], "mh_checksum": "%016x" % mh["checksum"],
         "golden": os.path.relpath(GOLDEN_CHECKSUMS, ROOT) if golden else None,
         "note": "sum over all ranks' slabs of value[k] * w(global pair index k) mod 2^64 (+ the MinHash count histogram) against "

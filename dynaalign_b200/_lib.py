@@ -85,6 +85,9 @@ _SIGS = {
     "dyna_quantile_type7_identities": (C.c_int, [C.POINTER(C.c_uint64), C.c_int64, C.c_int64, C.c_double, _f64p]),
     "dyna_nw_plan_threshold_edges": (C.c_int, [C.c_void_p, _i32p, C.c_int64, C.c_double, C.c_int64, _i32p, _i32p, _u32p, _u32p,
                                               _i64p, C.c_void_p]),
+    "dyna_nw_plan_layout": (C.c_void_p, [_u8p, _i64p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64]),
+    "dyna_nw_plan_unit_count": (C.c_int64, [C.c_void_p]),
+    "dyna_nw_plan_export_units": (C.c_int, [C.c_void_p, _i32p]),
     "dyna_nw_plan_pairs": (C.c_int64, [C.c_void_p]),
     "dyna_nw_plan_cells": (C.c_int64, [C.c_void_p]),
     "dyna_nw_plan_launches": (C.c_int, [C.c_void_p]),

@@ -888,6 +888,8 @@ struct NwClass {
 
 constexpr int kNwSideStreams = 3;
 
+constexpr int kNwLayoutOnly = -12345;  // `device` of a plan that only holds the work units (dyna_nw_plan_layout)
+
 struct dyna_nw_plan {
   int device = 0;
   int64_t n = 0, row_begin = 0, row_end = 0, pairs = 0, cells = 0;
@@ -910,6 +912,7 @@ struct dyna_nw_plan {
   cudaEvent_t ev_fork = nullptr, ev_join[kNwSideStreams] = {nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;  // synchronised before any buffer is released (see DevBuf)
   ~dyna_nw_plan() {
+    if (device == kNwLayoutOnly) return;  // never touched a device
     cudaStreamSynchronize(last_stream);
     for (int i = 0; i < kNwSideStreams; ++i) {
       if (side[i]) cudaStreamSynchronize(side[i]), cudaStreamDestroy(side[i]);
@@ -954,7 +957,8 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     return nullptr;
   }
   timer.lap("nw plan: validation");
-  if (use_device(device) != DYNA_OK) return nullptr;
+  const bool layout_only = (device == kNwLayoutOnly);  // dyna_nw_plan_layout: the work units only, no device touched
+  if (!layout_only && use_device(device) != DYNA_OK) return nullptr;
   timer.lap("nw plan: device");
 
   std::unique_ptr<dyna_nw_plan> p(new dyna_nw_plan);
@@ -1176,6 +1180,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   std::stable_sort(p->classes.begin(), p->classes.end(),
                    [](const std::unique_ptr<NwClass>& a, const std::unique_ptr<NwClass>& b) { return a->work > b->work; });
   timer.lap("nw plan: work units");
+  if (layout_only) return p.release();
   if (p->codes.alloc(codes.size()) || p->off.alloc(off32.size()) || p->sub.alloc(576) ||
       p->matches.alloc((size_t)p->pairs) || p->length.alloc((size_t)p->pairs))
     return nullptr;
@@ -1493,12 +1498,41 @@ extern "C" int dyna_nw_plan_threshold_edges(dyna_nw_plan* p, const int32_t* memb
   return DYNA_OK;
 }
 
+// The planner's decisions without a device (host logic only; tests/test_nw_planner_host.py checks that the units of every
+// class together cover each pair of the row range exactly once).
+extern "C" dyna_nw_plan* dyna_nw_plan_layout(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                                             int gap_open, int gap_ext, int64_t row_begin, int64_t row_end) {
+  return dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, kNwLayoutOnly);
+}
+extern "C" int64_t dyna_nw_plan_unit_count(const dyna_nw_plan* p) {
+  int64_t c = 0;
+  if (p) for (const auto& cl : p->classes) c += (int64_t)cl->units.size();
+  return c;
+}
+// out: 6 values per unit -- kernel kind (NwClass::kind), strip height R, row, second row (two-rows kinds; else -1),
+// first column, column count
+extern "C" int dyna_nw_plan_export_units(const dyna_nw_plan* p, int32_t* out) {
+  if (!p || !out) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_export_units: null argument");
+  for (const auto& cl : p->classes) {
+    const bool two_rows = cl->kind >= 8 && cl->kind <= 10;
+    for (const NwUnit& un : cl->units) {
+      *out++ = cl->kind;
+      *out++ = cl->R;
+      *out++ = un.row;
+      *out++ = two_rows ? un.row + (un.j_count >> 16) : -1;
+      *out++ = un.j_begin;
+      *out++ = two_rows ? (un.j_count & 0xFFFF) : un.j_count;
+    }
+  }
+  return DYNA_OK;
+}
+
 extern "C" int64_t dyna_nw_plan_pairs(const dyna_nw_plan* p) { return p ? p->pairs : 0; }
 extern "C" int64_t dyna_nw_plan_cells(const dyna_nw_plan* p) { return p ? p->cells : 0; }
 extern "C" int dyna_nw_plan_launches(const dyna_nw_plan* p) { return p ? p->launches : 0; }
 extern "C" void dyna_nw_plan_destroy(dyna_nw_plan* p) {
   if (!p) return;
-  cudaSetDevice(p->device);
+  if (p->device != kNwLayoutOnly) cudaSetDevice(p->device);
   delete p;
 }
 

@@ -234,6 +234,14 @@ DYNA_API int dyna_quantile_type7_identities(const uint64_t* hist, int64_t mdim, 
 DYNA_API int dyna_nw_plan_threshold_edges(dyna_nw_plan*, const int32_t* members, int64_t n_members, double threshold,
                                  int64_t max_edges, int32_t* i_out, int32_t* j_out, uint32_t* matches_out,
                                  uint32_t* length_out, int64_t* n_edges_out, void* stream);
+/* The planner's work units without touching a device (host logic only): which kernel family and strip height every
+ * (row | row pair) x column block of the triangle goes to.  The returned plan supports only unit_count / export_units /
+ * pairs / cells / destroy.  export_units writes 6 int32 per unit: kind, R, row, second row (-1 for single-row kinds),
+ * first column, column count. */
+DYNA_API dyna_nw_plan* dyna_nw_plan_layout(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                                  int gap_open, int gap_ext, int64_t row_begin, int64_t row_end);
+DYNA_API int64_t dyna_nw_plan_unit_count(const dyna_nw_plan*);
+DYNA_API int dyna_nw_plan_export_units(const dyna_nw_plan*, int32_t* out6);
 DYNA_API int64_t dyna_nw_plan_pairs(const dyna_nw_plan*);
 DYNA_API int64_t dyna_nw_plan_cells(const dyna_nw_plan*); /* sum of len_i*len_j over the plan's pairs */
 DYNA_API int dyna_nw_plan_launches(const dyna_nw_plan*);
