@@ -1803,20 +1803,104 @@ extern "C" int dyna_nw_pair_stats(const uint8_t* residues, const int64_t* offset
 }
 
 // dyna_nw_pair_stats with the narrow result form of dyna_nw_plan_fetch_packed8 (2 bytes per pair)
-extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
-                                   int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint8_t* matches8_out,
-                                   uint8_t* length8_out) {
-  dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, g_device);
-  if (!p) return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA;
-  int rc = dyna_nw_plan_run(p, nullptr);
-  if (rc == DYNA_OK) rc = dyna_nw_plan_fetch_packed8(p, matches8_out, length8_out, nullptr);
-  dyna_nw_plan_destroy(p);
-  return rc;
-}
-
 namespace {
 int plan_error_code() { return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA; }  // code of the failed plan creation
 }  // namespace
+
+extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
+                                   int gap_open, int gap_ext, int64_t row_begin, int64_t row_end, uint8_t* matches8_out,
+                                   uint8_t* length8_out) {
+  // Large row ranges go in row blocks of equal DP cells, pipelined: while block k is aligned on one stream, block k-1 is
+  // narrowed to bytes and copied to the host on another (the 100,000-peptide target: 0.29 s of kernels and 10 GB = 0.2 s
+  // of PCIe no longer add up), and the host builds the plan of block k+1.  At most three blocks hold device memory.
+  const int64_t total_pairs = (n >= 0 && row_begin >= 0 && row_end <= n && row_begin <= row_end)
+                                  ? tri_diag_rows(n, row_end) - tri_diag_rows(n, row_begin) : 0;
+  int blocks = total_pairs >= (64ll << 20) ? 8 : 1;
+  if (const char* e = getenv("DYNA_NW_STATS8_BLOCKS")) blocks = std::max(1, std::min(64, atoi(e)));
+  if (blocks == 1 || check_offsets(offsets, n, "dyna_nw_pair_stats8") != DYNA_OK) {
+    dyna_nw_plan* p = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, row_begin, row_end, g_device);
+    if (!p) return err_code_slot() ? err_code_slot() : DYNA_ERR_CUDA;
+    int rc = dyna_nw_plan_run(p, nullptr);
+    if (rc == DYNA_OK) rc = dyna_nw_plan_fetch_packed8(p, matches8_out, length8_out, nullptr);
+    dyna_nw_plan_destroy(p);
+    return rc;
+  }
+  // row bounds: equal shares of sum_i len_i * (sum_{j >= i} len_j)  (+ one per pair, so that empty sequences count)
+  std::vector<int64_t> bounds((size_t)blocks + 1, row_end);
+  {
+    std::vector<double> suffix((size_t)n + 1, 0.0);
+    for (int64_t i = n - 1; i >= 0; --i) suffix[(size_t)i] = suffix[(size_t)i + 1] + (double)(offsets[i + 1] - offsets[i]) + 1.0;
+    double total = 0.0;
+    for (int64_t i = row_begin; i < row_end; ++i) total += ((double)(offsets[i + 1] - offsets[i]) + 1.0) * suffix[(size_t)i];
+    double acc = 0.0;
+    int b = 1;
+    bounds[0] = row_begin;
+    for (int64_t i = row_begin; i < row_end && b < blocks; ++i) {
+      acc += ((double)(offsets[i + 1] - offsets[i]) + 1.0) * suffix[(size_t)i];
+      while (b < blocks && acc >= total * b / blocks) bounds[(size_t)b++] = i + 1;
+    }
+  }
+  DYNA_TRY(use_device(g_device));
+  struct Block {
+    dyna_nw_plan* plan = nullptr;
+    DevBuf<uint8_t> m8, l8;
+    cudaEvent_t done = nullptr;
+  };
+  std::vector<Block> blk((size_t)blocks);
+  cudaStream_t sc = nullptr, sd = nullptr;
+  cudaEvent_t ran = nullptr;
+  int rc = DYNA_OK;
+  auto cu = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == DYNA_OK) rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: dyna_nw_pair_stats8: %s", cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  auto retire = [&](Block& b) {  // wait for the block's copies, then hand its device memory back
+    if (b.done) {
+      cudaEventSynchronize(b.done);
+      cudaEventDestroy(b.done);
+      b.done = nullptr;
+    }
+    b.m8.release();
+    b.l8.release();
+    if (b.plan) dyna_nw_plan_destroy(b.plan);
+    b.plan = nullptr;
+  };
+  cu(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+  cu(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  cu(cudaEventCreateWithFlags(&ran, cudaEventDisableTiming));
+  const int64_t first = tri_diag_rows(n, row_begin);
+  for (int k = 0; k < blocks && rc == DYNA_OK; ++k) {
+    const int64_t rb = bounds[(size_t)k], re = bounds[(size_t)k + 1];
+    if (re <= rb) continue;
+    if (k >= 3) retire(blk[(size_t)k - 3]);
+    Block& b = blk[(size_t)k];
+    b.plan = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, rb, re, g_device);
+    if (!b.plan) { rc = plan_error_code(); break; }
+    if (2 * (int64_t)b.plan->max_cols > 255) {
+      rc = fail(DYNA_ERR_UNSUPPORTED, "dyna_nw_pair_stats8: alignment lengths up to %lld do not fit one byte", 2 * (long long)b.plan->max_cols);
+      break;
+    }
+    if ((rc = dyna_nw_plan_run(b.plan, sc)) != DYNA_OK) break;
+    const int64_t bp = b.plan->pairs, at = tri_diag_rows(n, rb) - first;
+    if (bp <= 0) continue;
+    if (b.m8.alloc((size_t)bp) || b.l8.alloc((size_t)bp)) { rc = DYNA_ERR_CUDA; break; }
+    cu(cudaEventRecord(ran, sc));
+    cu(cudaStreamWaitEvent(sd, ran, 0));
+    if ((rc = launch_nw_pack8(b.plan->matches.p, b.plan->length.p, bp, b.m8.p, b.l8.p, sd)) != DYNA_OK) break;
+    cu(cudaMemcpyAsync(matches8_out + at, b.m8.p, (size_t)bp, cudaMemcpyDeviceToHost, sd));
+    cu(cudaMemcpyAsync(length8_out + at, b.l8.p, (size_t)bp, cudaMemcpyDeviceToHost, sd));
+    cu(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+    cu(cudaEventRecord(b.done, sd));
+    b.plan->last_stream = sc;
+  }
+  if (sc) cudaStreamSynchronize(sc);
+  if (sd) cudaStreamSynchronize(sd);
+  for (auto& b : blk) retire(b);
+  if (ran) cudaEventDestroy(ran);
+  if (sc) cudaStreamDestroy(sc);
+  if (sd) cudaStreamDestroy(sd);
+  return rc;
+}
 
 extern "C" int dyna_similarityNW(const uint8_t* residues, const int64_t* offsets, int64_t n, const char* matrix_name,
                                  int gap_open, int gap_ext, double* out, int n_gpus) {

@@ -3,6 +3,8 @@ n x n double matrix, the position-weighted slab checksums, and the narrow host f
 with escapes) -- each against the oracle or against the wide form it must reproduce exactly."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -75,6 +77,29 @@ def test_nw_packed8_equals_wide_form():
     with pytest.raises(da.DynaAlignError) as e:
         da.nw_pair_stats8(peps + ["A" * 200])
     assert e.value.code == _lib.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("blocks", [2, 5, 64])
+def test_nw_packed8_pipelined_row_blocks(blocks):
+    # large row ranges are aligned block by block while the previous block is narrowed and copied (forced here on a small input)
+    rng = np.random.default_rng(80 + blocks)
+    peps = random_seqs(rng, 300, 0, 24) + ["", "", "AAAA"]
+    wm, wl = port.nw_pair_stats(peps)
+    os.environ["DYNA_NW_STATS8_BLOCKS"] = str(blocks)
+    try:
+        m8, l8 = da.nw_pair_stats8(peps)
+        assert (m8 == wm).all() and (l8 == wl).all()
+        m8, l8 = da.nw_pair_stats8(peps, row_begin=37, row_end=250)
+        wm, wl = port.nw_pair_stats(peps, row_begin=37, row_end=250)
+        assert (m8 == wm).all() and (l8 == wl).all()
+        m8, l8 = da.nw_pair_stats8(peps, row_begin=301, row_end=303)   # fewer rows than blocks
+        wm, wl = port.nw_pair_stats(peps, row_begin=301, row_end=303)
+        assert (m8 == wm).all() and (l8 == wl).all()
+        with pytest.raises(da.DynaAlignError) as e:
+            da.nw_pair_stats8(peps + ["A" * 200])
+        assert e.value.code == _lib.ERR_UNSUPPORTED
+    finally:
+        del os.environ["DYNA_NW_STATS8_BLOCKS"]
 
 
 def test_mh_fetch8_with_escapes_is_lossless():
