@@ -1146,11 +1146,15 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     const int m = (int)(offsets[i + 1] - offsets[i]);
     const int fam = family_of(m);
     int64_t i2 = -1;
-    if (fam != 0) {
+    if (fam != 0) {  // the compatible row of the closest length inside the window (ties: the nearest)
+      int64_t best = INT64_MAX;
       for (int64_t q = i + 1; q < std::min<int64_t>(i + 1 + pair_window, row_end); ++q) {
         if (covered[(size_t)(q - row_begin)]) continue;
         const int mq = (int)(offsets[q + 1] - offsets[q]);
-        if (family_of(mq) == fam && compatible(fam, m, mq)) { i2 = q; break; }
+        if (family_of(mq) != fam || !compatible(fam, m, mq)) continue;
+        // strips follow the longer row: what counts is the padding of the shorter one, in strip rows per lane
+        const int64_t cost = (int64_t)std::abs(m - mq) * 4096 + (q - i);
+        if (cost < best) { best = cost; i2 = q; }
       }
     }
     if (i2 < 0) {
