@@ -879,7 +879,7 @@ struct NwClass {
   int kind;  // 0 empty rows, 1 thread kernel, 2 warp kernel, 3 warp multipass, 4 two-pairs-per-warp 16-bit, 5 two-pairs-per-thread 16-bit,
              // 6 two-pairs-per-warp 16-bit, several passes, 7 two-pairs-per-warp-pair 16-bit (cooperating warps),
              // 8 two ROWS per warp 16-bit (units[].row and row+1 against the same column sequences), 9 its cooperative form,
-             // 10 two rows per thread (short probes)
+             // 10 two rows per thread (short probes), 12 two rows per warp, several passes (rows 769..3072)
   int R;
   int64_t work = 0;  // DP cells of the class (launch order: largest first)
   std::vector<NwUnit> units;
@@ -1022,6 +1022,11 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // (BASELINE config 2: 3337 GCUPS against 3291 at 64 and 3207 at 32 columns)
   bool use_rows2co = use_co;
   if (const char* e = getenv("DYNA_NW_ROWS2CO")) use_rows2co = use_rows2co && atoi(e) != 0;
+  // row pairs beyond the cooperative form: the two-rows multi-pass kernel (DYNA_NW_ROWS2MP=0: one row against two columns)
+  bool use_rows2mp = pack16;
+  if (const char* e = getenv("DYNA_NW_ROWS2MP")) use_rows2mp = use_rows2mp && atoi(e) != 0;
+  int rows2mp_cols = 64;  // four rounds of 16 column sequences: its units are long (several passes), keep them many
+  if (const char* e = getenv("DYNA_NW_ROWS2MP_COLS")) rows2mp_cols = std::min(kNwRows2UnitCols, std::max(16, atoi(e)));
   int rows2co_cols = kNwCoUnitCols;
   if (const char* e = getenv("DYNA_NW_ROWS2CO_COLS")) rows2co_cols = std::min(kNwCoUnitCols, std::max(1, atoi(e)));
   int warp2_cols = p->pairs >= (int64_t)kNwWarp2UnitColsMax * kNwMultiPassGrid * 32 ? kNwWarp2UnitColsMax : kNwWarp2UnitCols;
@@ -1124,18 +1129,22 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   // sequences j >= i2; the columns i <= j < i2 exist for row i only (that half is computed and dropped: at most the
   // window's width of them).  The decision is per UNIT: a unit whose longest column sequence leaves the 16-bit range or
   // the staging buffer is handed to the single-row path for both rows, the other units of the pair keep the fast kernel.
-  // family: 1 short probes (nw_thread_rows2_kernel), 2 rows 33..384 (nw_rows2_kernel), 3 rows 385..768 (nw_rows2co_kernel)
+  // family: 1 short probes (nw_thread_rows2_kernel), 2 rows 33..384 (nw_rows2_kernel), 3 rows 385..768 (nw_rows2co_kernel),
+  // 4 rows 769..3072 (nw_rows2mp_kernel)
   auto family_of = [&](int m) -> int {
     if (force_warp2) return 0;
     if (use_trows2 && m >= 1 && m <= kNwThreadMaxRows) return 1;
     if (use_rows2 && m > kNwThreadMaxRows && m <= 32 * 12) return 2;
     if (use_rows2co && m >= kNwCoMinRows && m <= kNwRows2CoMaxRows && nw_co_R(m) >= 7) return 3;
+    if (use_rows2mp && p->bias16 != 0u && m > kNwRows2CoMaxRows && m <= kNwRows2MpMaxRows) return 4;
     return 0;
   };
   auto compatible = [&](int fam, int ma, int mb) -> bool {
     const int mx = std::max(ma, mb), mn = std::min(ma, mb);
     if (fam == 1) return true;
     if (fam == 2) return 4 * mn >= 3 * mx;
+    if (fam == 4)  // multi-pass form: both rows end in the last pass of 32*R rows
+      return 4 * mn >= 3 * mx && (mn - 1) / (32 * nw_rows2mp_R(mx)) == (mx - 1) / (32 * nw_rows2mp_R(mx));
     // cooperative form: both rows reach into the second warp's block of 32*R rows
     return nw_co_R(mx) >= 7 && (mn - 1) / (32 * nw_co_R(mx)) == 1;
   };
@@ -1145,6 +1154,7 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
   int pair_window = (int)std::min<int64_t>(32, std::max<int64_t>(1, n / 96));
   if (const char* e = getenv("DYNA_NW_PAIR_WINDOW")) pair_window = std::min(4096, std::max(1, atoi(e)));
   std::vector<uint8_t> covered((size_t)(row_end - row_begin), 0);
+  auto plan_units = [&]() {
   for (int64_t i = row_begin; i < row_end; ++i) {
     if (covered[(size_t)(i - row_begin)]) continue;
     const int m = (int)(offsets[i + 1] - offsets[i]);
@@ -1168,20 +1178,42 @@ extern "C" dyna_nw_plan* dyna_nw_plan_create(const uint8_t* residues, const int6
     covered[(size_t)(i2 - row_begin)] = 1;
     const int m2 = (int)(offsets[i2 + 1] - offsets[i2]);
     const int mx = std::max(m, m2);
-    const int kind = fam == 1 ? 10 : fam == 2 ? 8 : 9;
-    const int R = fam == 1 ? nw_thread_R(mx) : fam == 2 ? nw_warp_R(mx) : nw_co_R(mx);
-    const int cols = fam == 1 ? 2 * kNwThreadUnitPairs : fam == 2 ? rows2_cols : rows2co_cols;
+    const int kind = fam == 1 ? 10 : fam == 2 ? 8 : fam == 3 ? 9 : 12;
+    const int R = fam == 1 ? nw_thread_R(mx) : fam == 2 ? nw_warp_R(mx) : fam == 3 ? nw_co_R(mx) : nw_rows2mp_R(mx);
+    const int cols = fam == 1 ? 2 * kNwThreadUnitPairs : fam == 3 ? rows2co_cols : fam == 4 ? rows2mp_cols : rows2_cols;
     NwClass* cls = get_class(kind, R);
     for (int64_t j = i; j < n; j += cols) {
       const int64_t cnt = std::min<int64_t>(cols, n - j);
       const int64_t nmax = range_max(j, j + cnt);
-      if (fits16u(mx, nmax) && (fam == 1 || nmax <= (fam == 2 ? kNwRows2MaxCols : nw_rows2co_max_cols(R)))) {
+      if (fits16u(mx, nmax) && (fam == 1 || nmax <= (fam == 3 ? nw_rows2co_max_cols(R) : kNwRows2MaxCols))) {
+        if (fam == 4) need_scratch2 = true;
         cls->units.push_back(NwUnit{(int32_t)i, (int32_t)j, nw_pack_count(cnt, i2 - i)});
         cls->work += (int64_t)(m + m2) * (len_prefix[(size_t)(j + cnt)] - len_prefix[(size_t)j] + cnt);
       } else {
         emit_single(i, j, j + cnt);
         if (j + cnt > i2) emit_single(i2, std::max(j, i2), j + cnt);
       }
+    }
+  }
+  };
+  plan_units();
+  // The two-rows multi-pass kernel runs as one persistent CTA per SM with long units: as a small class next to the
+  // others it costs more in its tail than it gains (length mix, n = 3000, 5 % of the cells: 2880 vs 2974 GCUPS without;
+  // long proteins, 99 % of the cells: 3378 vs 2629).  Below a tenth of the plan's cells its rows go back to the one-row
+  // multi-pass kernel.
+  if (use_rows2mp && !getenv("DYNA_NW_ROWS2MP")) {
+    int64_t total = 0, mp = 0;
+    for (const auto& cl : p->classes) {
+      total += cl->work;
+      if (cl->kind == 12) mp += cl->work;
+    }
+    if (mp > 0 && mp * 10 < total) {
+      use_rows2mp = false;
+      p->classes.clear();
+      by_key.clear();
+      need_scratch = need_scratch2 = false;
+      std::fill(covered.begin(), covered.end(), (uint8_t)0);
+      plan_units();
     }
   }
 
@@ -1246,7 +1278,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
   if (fork) DYNA_CUDA(cudaEventRecord(p->ev_fork, st));
   int next_side = 0;
   bool first = true;
-  cudaStream_t kind_stream[8] = {};
+  cudaStream_t kind_stream[8] = {};  // indexed by the scratch owner: 3, or 6 (kinds 6 and 12 share scratch2)
   bool kind_stream_set[8] = {};
   for (auto& c : p->classes) {
     const int nu = (int)c->units.size();
@@ -1254,9 +1286,10 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
     cudaStream_t cs = st;
     // the two multi-pass kernels keep per-plan scratch lines: all classes of one such kind share ONE stream (which is
     // the caller's stream if the largest class happens to be of that kind)
-    const bool scratch_kind = (c->kind == 3 || c->kind == 6);
-    if (scratch_kind && kind_stream_set[c->kind]) {
-      cs = kind_stream[c->kind];
+    const bool scratch_kind = (c->kind == 3 || c->kind == 6 || c->kind == 12);
+    const int sk = c->kind == 12 ? 6 : c->kind;
+    if (scratch_kind && kind_stream_set[sk]) {
+      cs = kind_stream[sk];
     } else if (fork && !first) {
       const int si = next_side++ % kNwSideStreams;
       if (!used[si]) DYNA_CUDA(cudaStreamWaitEvent(p->side[si], p->ev_fork, 0));
@@ -1264,8 +1297,8 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       cs = p->side[si];
     }
     if (scratch_kind) {
-      kind_stream_set[c->kind] = true;
-      kind_stream[c->kind] = cs;
+      kind_stream_set[sk] = true;
+      kind_stream[sk] = cs;
     }
     first = false;
     switch (c->kind) {
@@ -1279,6 +1312,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
       case 8: DYNA_TRY(launch_nw_rows2(c->R, d, c->d_units.p, nu, cs)); break;
       case 9: DYNA_TRY(launch_nw_rows2co(c->R, d, c->d_units.p, nu, cs)); break;
       case 10: DYNA_TRY(launch_nw_thread_rows2(c->R, d, c->d_units.p, nu, cs)); break;
+      case 12: DYNA_TRY(launch_nw_rows2mp(c->R, d, c->d_units.p, nu, p->scratch2.p, cs)); break;
       default: DYNA_TRY(launch_nw_warp(c->R, p->slant, true, d, c->d_units.p, nu, p->scratch.p, p->max_cols, cs)); break;
     }
     ++p->launches;
@@ -1522,7 +1556,7 @@ extern "C" int64_t dyna_nw_plan_unit_count(const dyna_nw_plan* p) {
 extern "C" int dyna_nw_plan_export_units(const dyna_nw_plan* p, int32_t* out) {
   if (!p || !out) return fail(DYNA_ERR_INVALID, "dyna_nw_plan_export_units: null argument");
   for (const auto& cl : p->classes) {
-    const bool two_rows = cl->kind >= 8 && cl->kind <= 10;
+    const bool two_rows = (cl->kind >= 8 && cl->kind <= 10) || cl->kind == 12;
     for (const NwUnit& un : cl->units) {
       *out++ = cl->kind;
       *out++ = cl->R;

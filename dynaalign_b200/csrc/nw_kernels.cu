@@ -1082,6 +1082,283 @@ nw_rows2_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5x2 "two rows", multi-pass: row pairs longer than the cooperative form holds (769..3072 residues).  The rows are walked
+// in passes of 32*R rows with the strip code of nw_rows2_kernel; lane 31's bottom row (H, F', both statistics: 16 bytes per
+// column) goes through a per-warp global scratch line (in place: lane 31 is 31 columns behind lane 0).  Lane 0 of the next
+// pass does not load it from global memory step by step -- an L2 round trip is longer than a step of this kernel's four
+// warps per scheduler, the first version ran at 2.67 TCUPS with the warp waiting for lane 0 in every step of passes 1.. --
+// the warp copies it 32 entries at a time with cp.async into a 64-entry shared-memory ring, one block (32 steps) ahead, and
+// lane 0 overwrites its four shuffled registers with one predicated 128-bit shared load (pass 0: a ring of border entries).  The record table belongs to one pass and to the whole CTA, so the 16
+// warps move through the passes together: in every ROUND each warp takes ONE column sequence through all passes (the
+// table is rebuilt 16 times more often than with the passes outermost, ~2 % of the work, and the scratch is 32 KB per warp
+// instead of one line per column sequence of the unit).
+// Records: three words per row (scores, increment of pair 1, increment of pair 2) and statistics words matches << 16 |
+// diagonal steps -- the shared 10+10+12-bit increment of the single-pass kernels stops at 1023 diagonal steps.
+// Host: both rows end in the last pass, 4 * shorter >= 3 * longer, columns <= kNwRows2MaxCols, unsigned domain.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+struct Rec3 {
+  static constexpr int kWords = 3 * R;
+  static constexpr int NQ = (kWords + 3) / 4;
+  static constexpr int kStride = (NQ | 1) * 4;
+  static constexpr int kTableBytes = 24 * 32 * kStride * 4;
+  static constexpr int kStageBytes = (kRows2Threads / 32) * (kNwRows2MaxCols + 8);
+  static constexpr int kRingBytes = (kRows2Threads / 32) * 64 * 16;  // per warp: 64 boundary entries of 16 bytes
+  static constexpr int kTotal = kTableBytes + kStageBytes + kRingBytes;
+  __host__ __device__ static constexpr int first_needed(int q) { return (4 * q) / 3; }
+  __host__ __device__ static constexpr int load_row(int q) {
+    return first_needed(q) >= DYNA_ROWS2_LOOKAHEAD ? first_needed(q) - DYNA_ROWS2_LOOKAHEAD : 0;
+  }
+};
+
+// rows [0, 32R) of the pass: a1 / a2 point at the pass's first row, m1 / m2 are what is left of the sequences (<= 0: none)
+template <int R, bool U>
+__device__ __forceinline__ void build_records3(uint32_t* rec, const uint8_t* __restrict__ a1, int m1,
+                                               const uint8_t* __restrict__ a2, int m2, const int8_t* __restrict__ sub, int bias,
+                                               int tid, int nthreads) {
+  using RC = Rec3<R>;
+  for (int idx = tid; idx < 24 * 32 * RC::kStride; idx += nthreads) {
+    const int cls = idx / (32 * RC::kStride);
+    const int rem = idx - cls * (32 * RC::kStride);
+    const int ln = rem / RC::kStride, w = rem - ln * RC::kStride;
+    uint32_t v = 0u;
+    if (w < RC::kWords) {
+      const int k = w / 3, t = w - 3 * k, r = ln * R + k;
+      if (t == 0) {
+        const int s1 = r < m1 ? (int)(int8_t)(sub[a1[r] * 24 + cls] + bias) : 0;
+        const int s2 = r < m2 ? (int)(int8_t)(sub[a2[r] * 24 + cls] + bias) : 0;
+        v = score2_word(s1, s2, U);
+      } else if (t == 1) {
+        v = 1u | ((r < m1 && a1[r] == cls) ? 0x10000u : 0u);
+      } else {
+        v = 1u | ((r < m2 && a2[r] == cls) ? 0x10000u : 0u);
+      }
+    }
+    rec[idx] = v;
+  }
+}
+
+// strip_column4 on three-word records (one increment per pair)
+template <int R, bool U>
+__device__ __forceinline__ void strip_column4x(const uint32_t (&Ho)[R], uint32_t (&Hn)[R], uint32_t (&El)[R],
+                                               const uint32_t (&SAo)[R], uint32_t (&SAn)[R], const uint32_t (&SBo)[R],
+                                               uint32_t (&SBn)[R], uint32_t rec_sh, uint32_t diagH, uint32_t dSA, uint32_t dSB,
+                                               uint32_t F, uint32_t upSA, uint32_t upSB, uint32_t ngo2, const Stat2Consts& c,
+                                               uint32_t& outF) {
+  using RC = Rec3<R>;
+  uint32_t w[RC::NQ * 4];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+#pragma unroll
+    for (int q = 0; q < RC::NQ; ++q) {
+      if (RC::load_row(q) == k) {
+        const uint4 v = lds_v4(rec_sh + 16u * (unsigned)q);
+        w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+    }
+    const uint32_t sP = w[3 * k], incA = w[3 * k + 1], incB = w[3 * k + 2];
+    const uint32_t E = El[k];
+    const uint32_t Mraw = U ? diagH + sP : __viaddmax_s16x2(diagH, sP, 0x80008000u);
+    bool puB, puA, pdB, pdA;
+    const uint32_t g = U ? __vibmax_u16x2(F, E, &puB, &puA) : __vibmax_s16x2(F, E, &puB, &puA);
+    const uint32_t H = U ? __vibmax_u16x2(Mraw, g, &pdB, &pdA) : __vibmax_s16x2(Mraw, g, &pdB, &pdA);
+    const uint32_t SA = ((DYNA_ROWS2_SELMASK_UA >> k) & 1) ? stat_select_sel(SAo[k], upSA, dSA, incA, puA, pdA)
+                                                           : stat_select(SAo[k], upSA, dSA, incA, puA, pdA, c.zero);
+    const uint32_t SB = ((DYNA_ROWS2_SELMASK_UB >> k) & 1) ? stat_select_sel(SBo[k], upSB, dSB, incB, puB, pdB)
+                                                           : stat_select(SBo[k], upSB, dSB, incB, puB, pdB, c.zero);
+    diagH = Ho[k];
+    dSA = SAo[k];
+    dSB = SBo[k];
+    Hn[k] = H;
+    SAn[k] = SA;
+    SBn[k] = SB;
+    El[k] = U ? __viaddmax_u16x2(H, ngo2, E) : __viaddmax_s16x2(H, ngo2, E);
+    F = U ? __viaddmax_u16x2(H, ngo2, F) : __viaddmax_s16x2(H, ngo2, F);
+    upSA = SA;
+    upSB = SB;
+  }
+  outF = F;
+}
+
+template <int R, bool U>
+__global__ void __launch_bounds__(kRows2Threads, 1)
+nw_rows2mp_kernel(NwDeviceData d, const NwUnit* __restrict__ units, int num_units, uint4* __restrict__ scratch) {
+  using RC = Rec3<R>;
+  constexpr int nwarps = kRows2Threads / 32;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  uint32_t* rec = reinterpret_cast<uint32_t*>(smem_dyn);
+  uint8_t* stage_base = smem_dyn + RC::kTableBytes;
+  __shared__ uint32_t res_m1[kNwRows2UnitCols], res_l1[kNwRows2UnitCols], res_m2[kNwRows2UnitCols], res_l2[kNwRows2UnitCols];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int go = d.gap_open, ge = d.gap_ext;
+  const uint32_t ngo2 = pack16(-go);
+  Stat2Consts c;
+  c.one = d.one;
+  c.zero = d.zero;
+  const uint32_t sent2 = (U ? 0u : pack16(kSentinel16)) + c.zero;
+  const uint32_t bord2 = pack16(ge - go + (U ? (int)d.bias16 : 0));
+  const uint32_t corner2 = U ? pack16((int)d.bias16) : 0u;
+  const unsigned full = 0xFFFFFFFFu;
+  uint8_t* sC = stage_base + warp * (kNwRows2MaxCols + 8);
+  const uint32_t sC_sh = (uint32_t)__cvta_generic_to_shared(sC);
+  const uint32_t rlane_sh = (uint32_t)__cvta_generic_to_shared(rec + lane * RC::kStride);
+  uint4* scr = scratch + ((int64_t)blockIdx.x * nwarps + warp) * kNwRows2MaxCols;
+  __shared__ int col_len[kNwRows2UnitCols];
+  __shared__ uint8_t col_ord[kNwRows2UnitCols];
+  static_assert(kNwRows2UnitCols <= 256 && kNwRows2UnitCols <= kRows2Threads, "column order: one byte, one thread per column");
+  static_assert((RC::kTableBytes + RC::kStageBytes) % 16 == 0, "ring alignment");
+  uint4* ring = reinterpret_cast<uint4*>(smem_dyn + RC::kTableBytes + RC::kStageBytes) + warp * 64;
+  const uint32_t ring_sh = (uint32_t)__cvta_generic_to_shared(ring);
+
+  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    NwUnit un = units[u];
+    const int row = un.row, row2 = row + (un.j_count >> 16);
+    un.j_count &= 0xFFFF;
+    const int m1 = d.off[row + 1] - d.off[row], m2 = d.off[row2 + 1] - d.off[row2];
+    const uint8_t* __restrict__ a1 = d.codes + d.off[row];
+    const uint8_t* __restrict__ a2 = d.codes + d.off[row2];
+    const int npass = (max(m1, m2) + 32 * R - 1) / (32 * R);
+    const int rounds = (un.j_count + nwarps - 1) / nwarps;
+    // the warps of a round wait for each other at every pass: the unit's column sequences are taken in order of length,
+    // so that a round holds 16 of about the same length (a proteome-like mix ran at 40 % efficiency in input order)
+    __syncthreads();
+    if (tid < un.j_count) col_len[tid] = d.off[un.j_begin + tid + 1] - d.off[un.j_begin + tid];
+    __syncthreads();
+    if (tid < un.j_count) {
+      const int mine = col_len[tid];
+      int rank = 0;
+      for (int q = 0; q < un.j_count; ++q) {
+        const int other = col_len[q];
+        rank += (other > mine || (other == mine && q < tid)) ? 1 : 0;
+      }
+      col_ord[rank] = (uint8_t)tid;
+    }
+    __syncthreads();
+
+    for (int rd = 0; rd < rounds; ++rd) {
+      const bool has = rd * nwarps + warp < un.j_count;
+      const int pp = has ? (int)col_ord[rd * nwarps + warp] : 0;
+      int n = 0;
+      if (has) {
+        const int j = un.j_begin + pp;
+        n = d.off[j + 1] - d.off[j];
+        const uint8_t* __restrict__ b = d.codes + d.off[j];
+        __syncwarp();
+        for (int q = lane; q < n; q += 32) sC[q] = b[q];
+        __syncwarp();
+      }
+      for (int pass = 0; pass < npass; ++pass) {
+        const int row0 = pass * 32 * R;
+        const bool last = (pass == npass - 1);
+        __syncthreads();  // nobody reads the previous pass's table any more
+        build_records3<R, U>(rec, a1 + row0, m1 - row0, a2 + row0, m2 - row0, d.sub, 2 * ge, tid, kRows2Threads);
+        __syncthreads();
+        if (!has) continue;
+        const int lmA = last ? (m1 - 1 - row0) / R : 31, kmA = (m1 - 1 - row0) - lmA * R;
+        const int lmB = last ? (m2 - 1 - row0) / R : 31, kmB = (m2 - 1 - row0) - lmB * R;
+        const int lm = max(lmA, lmB);
+        uint32_t H0[R], H1[R], El[R], SA0[R], SA1[R], SB0[R], SB1[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          H0[k] = H1[k] = bord2;
+          El[k] = sent2;
+          SA0[k] = SA1[k] = SB0[k] = SB1[k] = 0u;
+        }
+        uint32_t prevUpH = (row0 == 0 && lane == 0) ? corner2 : bord2;
+        uint32_t prevUpSA = 0u, prevUpSB = 0u;
+        uint32_t outF = sent2;
+        const unsigned n_act = (lane <= lm) ? (unsigned)n : 0u;
+        const int T = n + lm;
+        // what lane 0 sees above its first row, per column: ring entry (column & 63)
+        auto request = [&](int first) {  // the warp asks for scratch entries first .. first + 31 (those that exist)
+          const int idx = first + lane;
+          if (idx < n)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_sh + (uint32_t)(idx & 63) * 16u), "l"(scr + idx));
+          asm volatile("cp.async.commit_group;");
+        };
+        __syncwarp();
+        if (pass == 0) {
+          ring[lane] = make_uint4(bord2, sent2, 0u, 0u);
+          ring[lane + 32] = make_uint4(bord2, sent2, 0u, 0u);
+        } else {
+          request(0);
+          request(32);
+          asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncwarp();
+        for (int t0 = 0; t0 < T; t0 += 2) {
+          if (pass > 0 && (t0 & 31) == 0 && t0 > 0) {  // lane 0 enters block t0 / 32, requested 32 steps ago; ask for the next one
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            request(t0 + 32);
+          }
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int jc = t0 + ph - lane;
+            uint32_t rH = __shfl_up_sync(full, ph == 1 ? H1[R - 1] : H0[R - 1], 1);
+            uint32_t rF = __shfl_up_sync(full, outF, 1);
+            uint32_t rSA = __shfl_up_sync(full, ph == 1 ? SA1[R - 1] : SA0[R - 1], 1);
+            uint32_t rSB = __shfl_up_sync(full, ph == 1 ? SB1[R - 1] : SB0[R - 1], 1);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %4, 0;\n\t@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n\t}"
+                         : "+r"(rH), "+r"(rF), "+r"(rSA), "+r"(rSB)
+                         : "r"((uint32_t)lane), "r"(ring_sh + (uint32_t)((t0 + ph) & 63) * 16u)
+                         : "memory");
+            if ((unsigned)jc < n_act) {
+              const uint32_t cc = lds_u8(sC_sh + (uint32_t)jc);
+              const uint32_t ra = rlane_sh + cc * (32u * RC::kStride * 4u);
+              if (ph == 0) {
+                strip_column4x<R, U>(H0, H1, El, SA0, SA1, SB0, SB1, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              } else {
+                strip_column4x<R, U>(H1, H0, El, SA1, SA0, SB1, SB0, ra, prevUpH, prevUpSA, prevUpSB, rF, rSA, rSB, ngo2, c, outF);
+              }
+              if (!last && lane == 31)  // the bottom row just written (the other register set)
+                scr[jc] = ph == 0 ? make_uint4(H1[R - 1], outF, SA1[R - 1], SB1[R - 1])
+                                  : make_uint4(H0[R - 1], outF, SA0[R - 1], SB0[R - 1]);
+            }
+            prevUpH = rH;
+            prevUpSA = rSA;
+            prevUpSB = rSB;
+          }
+        }
+        if (last) {
+          const bool in1 = (((lane + n) & 1) != 0);
+          uint32_t resA = 0u, resB = 0u;
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            if (k == kmA) resA = in1 ? SA1[k] : SA0[k];
+            if (k == kmB) resB = in1 ? SB1[k] : SB0[k];
+          }
+          resA = __shfl_sync(full, resA, lmA);
+          resB = __shfl_sync(full, resB, lmB);
+          if (lane == 0) {  // stat word: matches << 16 | diagonal steps;  length = m + n - diagonal steps
+            res_m1[pp] = resA >> 16;
+            res_l1[pp] = (uint32_t)(m1 + n) - (resA & 0xFFFFu);
+            res_m2[pp] = resB >> 16;
+            res_l2[pp] = (uint32_t)(m2 + n) - (resB & 0xFFFFu);
+          }
+        }
+        __syncwarp();  // lane 31's scratch entries of this pass before lane 0 reads them in the next
+      }
+    }
+    __syncthreads();
+    {
+      const int64_t slot1 = pair_slot(d.n, row, un.j_begin, d.slab_base);
+      const int skip = un.j_begin < row2 ? row2 - un.j_begin : 0;
+      const int64_t slot2 = pair_slot(d.n, row2, un.j_begin + skip, d.slab_base) - skip;
+      for (int q = tid; q < un.j_count; q += kRows2Threads) {
+        d.matches[slot1 + q] = res_m1[q];
+        d.length[slot1 + q] = res_l1[q];
+        if (q >= skip) {
+          d.matches[slot2 + q] = res_m2[q];
+          d.length[slot2 + q] = res_l2[q];
+        }
+      }
+    }
+    __syncthreads();  // res_* are rewritten by the next unit
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5x2 multi-pass: the packed two-pairs kernel for rows longer than one pass of 32*R rows (R <= 12 keeps the fast
 // ping-pong / increment-table configuration).  The CTA walks the row sequence in passes of 32*R rows; within a pass
 // every warp processes its pair-sets exactly like nw_warp2_kernel, except that
@@ -2297,6 +2574,30 @@ int launch_rows2_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, 
   }
   DYNA_CUDA(cudaGetLastError());
   return DYNA_OK;
+}
+
+template <int R>
+int launch_rows2mp_R(const NwDeviceData& d, const NwUnit* d_units, int num_units, uint4* scr, cudaStream_t st) {
+  using RC = Rec3<R>;
+  DYNA_CUDA(cudaFuncSetAttribute(nw_rows2mp_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RC::kTotal));
+  nw_rows2mp_kernel<R, true><<<std::min(num_units, kNwRows2MpGrid), kRows2Threads, RC::kTotal, st>>>(d, d_units, num_units, scr);
+  DYNA_CUDA(cudaGetLastError());
+  return DYNA_OK;
+}
+
+int launch_nw_rows2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, void* d_scratch, cudaStream_t st) {
+  if (num_units == 0) return DYNA_OK;
+  if (d.bias16 == 0u) return fail(DYNA_ERR_UNSUPPORTED, "nw two-rows multi-pass kernel: needs the unsigned 16-bit domain");
+  uint4* scr = static_cast<uint4*>(d_scratch);
+  switch (R) {
+#define DYNA_CASE(RR) \
+  case RR:            \
+    return launch_rows2mp_R<RR>(d, d_units, num_units, scr, st);
+    DYNA_CASE(7) DYNA_CASE(8) DYNA_CASE(9) DYNA_CASE(10) DYNA_CASE(11) DYNA_CASE(12)
+#undef DYNA_CASE
+    default:
+      return fail(DYNA_ERR_UNSUPPORTED, "nw two-rows multi-pass kernel: unsupported strip height %d", R);
+  }
 }
 
 int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st) {

@@ -71,6 +71,14 @@ int launch_nw_warp2co(int R, const NwDeviceData& d, const NwUnit* d_units, int n
 constexpr int kNwRows2UnitCols = 256;
 constexpr int kNwRows2MaxCols = 2048;  // its column-sequence length limit (one staged sequence per warp)
 int launch_nw_rows2(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, cudaStream_t st);
+// two-rows multi-pass kernel: row pairs of 769..kNwRows2MpMaxRows residues, both ending in the same (last) pass of 32*R rows,
+// R = nw_rows2mp_R(longer row) in 7..12; persistent grid of kNwRows2MpGrid CTAs of 16 warps; scratch: one line of
+// kNwRows2MaxCols 16-byte entries per warp (it fits the scratch of launch_nw_warp2mp and shares it: same stream)
+constexpr int kNwRows2MpMaxRows = 32 * 12 * 8;
+constexpr int kNwRows2MpGrid = 148;
+inline int nw_rows2mp_passes(int m) { return (m + 32 * 12 - 1) / (32 * 12); }
+inline int nw_rows2mp_R(int m) { const int np = nw_rows2mp_passes(m); const int r = (m + 32 * np - 1) / (32 * np); return r < 7 ? 7 : r; }
+int launch_nw_rows2mp(int R, const NwDeviceData& d, const NwUnit* d_units, int num_units, void* d_scratch, cudaStream_t st);
 // cooperative two-rows kernel: row pairs of 385..768 residues (R = ceil(max/64) <= 12); units of up to kNwCoUnitCols columns
 constexpr int kNwRows2CoMaxRows = 64 * 12;
 // its column-sequence length limit: the staging buffers share the SM's 227 KB with 172 KB of tables from R = 11 on

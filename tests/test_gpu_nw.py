@@ -119,6 +119,28 @@ def test_two_rows_kernels_long_columns_and_mixed_lengths(lo, hi):
         del os.environ["DYNA_NW_PAIR_WINDOW"]
 
 
+@pytest.mark.parametrize("lo,hi", [(769, 1000), (1000, 1152), (1153, 1536), (2000, 2304)])
+def test_two_rows_multipass_kernel(lo, hi):
+    # row pairs beyond the cooperative form (769..3072 residues): passes of 32*R rows, lane 31's bottom row through a
+    # per-warp scratch line (nw_rows2mp_kernel).  Related sequences (long diagonal runs across the pass boundaries),
+    # unrelated ones, rows that end in different passes (no pair), short and long columns, columns beyond the staging buffer.
+    rng = np.random.default_rng(lo + 3 * hi)
+    fam = "".join(random_seqs(rng, 1, hi, hi, "ARNDCQEGHILKMFPSTWYV"))
+    seqs = [fam[: int(L)] for L in rng.integers(lo, hi + 1, size=14)] + random_seqs(rng, 10, lo, hi, "ARNDCQEGHILKMFPSTWYV")
+    seqs += [fam[:hi], fam[3:hi], fam[:lo]] + random_seqs(rng, 8, 1, 400) + random_seqs(rng, 2, 2049, 2100) + [""]
+    rng.shuffle(seqs)
+    os.environ["DYNA_NW_ROWS2MP"] = "1"  # (by default only when these rows hold a tenth of the plan's cells: they do here)
+    try:
+        check_stats(seqs)
+        a = da.nw_pair_stats(seqs[:20], "BLOSUM80", 7, 1)
+        os.environ["DYNA_NW_ROWS2MP"] = "0"
+        b = da.nw_pair_stats(seqs[:20], "BLOSUM80", 7, 1)
+    finally:
+        del os.environ["DYNA_NW_ROWS2MP"]
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    check_stats(seqs[:24])
+
+
 def test_cooperative_kernel_equals_single_warp_kernels():
     # same input through the cooperative kernel and (DYNA_NW_CO=0) the tall-strip / multi-pass kernels
     rng = np.random.default_rng(77)

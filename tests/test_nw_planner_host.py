@@ -10,7 +10,7 @@ import pytest
 from dynaalign_b200._lib import flatten, lib, ptr
 
 AL = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
-TWO_ROW_KINDS = (8, 9, 10)
+TWO_ROW_KINDS = (8, 9, 10, 12)
 
 
 def layout(lens, table=b"BLOSUM62", go=10, ge=4, rb=0, re_=None, seed=0):
@@ -108,6 +108,19 @@ def test_random_mixes_and_row_slabs(seed):
 def test_penalties_outside_the_16_bit_range_use_the_32_bit_kernels():
     lens = [200, 210, 220, 500, 510, 20, 22]
     units = check_cover(lens, go=9000, ge=4)
-    assert not set(units[:, 0]) & {4, 5, 6, 7, 8, 9, 10}
+    assert not set(units[:, 0]) & {4, 5, 6, 7, 8, 9, 10, 12}
     check_cover(lens, go=0, ge=0)
     check_cover(lens, table=b"BLOSUM45", go=3, ge=1)
+
+
+def test_long_rows_take_the_two_rows_multipass_kernel():
+    rng = np.random.default_rng(9)
+    lens = np.concatenate([rng.integers(800, 1000, size=40), rng.integers(1200, 1500, size=20), rng.integers(100, 300, size=30)])
+    rng.shuffle(lens)
+    units = check_cover(lens)
+    k12 = units[units[:, 0] == 12]
+    assert len(k12) > 0
+    R = k12[:, 1]
+    for kind, r, row, row2, j0, cnt in k12:
+        a, b = sorted((int(lens[row]), int(lens[row2])))
+        assert 7 <= r <= 12 and (a - 1) // (32 * r) == (b - 1) // (32 * r), "both rows end in the same pass"
