@@ -569,17 +569,22 @@ def phase_mh(ctx):
 
 
 # ================================================================== NW on the 100,000 peptides (north_star target), all ranks
-def phase_mixed_nw(ctx):
-    """NW on a proteome-like length mix (log-normal, median 300 residues, a few sequences beyond 1024): what the planner
-    makes of rows that do not sit next to a row of their own length.  Rank 0 only; device time and an oracle sample."""
+def phase_mixed_nw(ctx, kind="mix"):
+    """NW on inputs whose rows are not all alike.  "mix": a proteome-like length mix (log-normal, median 300 residues, a
+    few sequences beyond 1024) -- what the planner makes of rows that do not sit next to a row of their own length.
+    "long": 1,500 proteins of 700..1020 residues -- the multi-pass kernels.  Rank 0 only; device time and an oracle sample."""
     if ctx.rank != 0:
         return None
     from dynaalign_b200._lib import flatten, ptr
     from dynaalign_b200 import synth
     L = ctx.L
     rng = np.random.default_rng(7)
-    n = 3000
-    lens = np.clip(rng.lognormal(np.log(300.0), 0.5, size=n), 30, 1800).astype(int)
+    if kind == "mix":
+        n = 3000
+        lens = np.clip(rng.lognormal(np.log(300.0), 0.5, size=n), 30, 1800).astype(int)
+    else:
+        n = 1500
+        lens = np.clip(np.rint(rng.normal(900.0, 60.0, size=n)), 700, 1020).astype(int)
     seqs = [synth.RESIDUES20[rng.integers(0, 20, size=int(x))].tobytes() for x in lens]
     res, off = flatten(seqs)
     plan = L.dyna_nw_plan_create(ptr(res, C.c_uint8), ptr(off, C.c_int64), n, b"BLOSUM62", 10, 4, 0, n, ctx.dev)
@@ -610,7 +615,7 @@ def phase_mixed_nw(ctx):
         ok = True
         order = np.argsort(lens)
         picks = [(int(order[-1 - k]), int(order[-40 - k])) for k in range(6)]            # long against long
-        picks += [(int(a), int(b)) for a, b in rng.integers(0, n, size=(150, 2))]
+        picks += [(int(a), int(b)) for a, b in rng.integers(0, n, size=(150 if kind == "mix" else 40, 2))]
         for a, b in picks:
             i, j = min(a, b), max(a, b)
             slot = i * n - i * (i - 1) // 2 + (j - i)
@@ -619,8 +624,11 @@ def phase_mixed_nw(ctx):
     ctx.release_memory()
     return {"n": n, "length_min_median_max": [int(lens.min()), int(np.median(lens)), int(lens.max())], "cells": int(cells),
             "seconds": ms * 1e-3, "gcups": cells / ms / 1e6, "kernel_launches_per_step": int(launches), "oracle_sample_ok": ok,
-            "note": "log-normal lengths (median 300, sigma 0.5, clipped to 30..1800), uniform residues, input order random: "
-                    "two-rows partner search in a 32-row window, kernel choice per unit, device time of dyna_nw_plan_run"}
+            "note": ("log-normal lengths (median 300, sigma 0.5, clipped to 30..1800), uniform residues, input order random: "
+                     "two-rows partner search in a 32-row window, kernel choice per unit, device time of dyna_nw_plan_run")
+                    if kind == "mix" else
+                    "lengths Normal(900, 60) clipped to 700..1020, uniform residues: rows of 769+ residues through the two-rows "
+                    "multi-pass kernel, the rest through the cooperative one; device time of dyna_nw_plan_run"}
 
 
 def phase_target_nw(ctx):
@@ -820,6 +828,11 @@ def main():
     except Exception as e:
         mixed = {"error": str(e)[:200]}
         ctx.release_memory()
+    try:
+        longp = phase_mixed_nw(ctx, "long")
+    except Exception as e:
+        longp = {"error": str(e)[:200]}
+        ctx.release_memory()
 
     # ---------------- the R-facing call on all N GPUs of the box, from rank 0 (headline e2e)
     e2e_steps = max(1, min(args.steps, 3))
@@ -860,6 +873,7 @@ def main():
         if other is not None:
             other["target_nw_100k_peptides"] = target
             other["nw_mixed_lengths_3000"] = mixed
+            other["nw_long_proteins_1500"] = longp
             other["similarityNW_inproc_n%d" % world] = {
                 "config5": {"n": n, "n_gpus": world, "seconds": inproc_s, "gcups": nw["total_cells"] / inproc_s / 1e9,
                             "d2h_bytes": 8 * n * n},
@@ -901,6 +915,7 @@ def main():
         "target_nw": cmp(key_tg, {"matches": target["checksum"][0], "length": target["checksum"][1]}) if "checksum" in target else None,
         "target_nw_oracle_sample": target.get("oracle_sample_ok"),
         "nw_mixed_lengths_oracle_sample": (mixed or {}).get("oracle_sample_ok"),
+        "nw_long_proteins_oracle_sample": (longp or {}).get("oracle_sample_ok"),
         "nw_checksum": ["%016x" % c for c in nw["checksum"]], "mh_checksum": "%016x" % mh["checksum"],
         "golden": os.path.relpath(GOLDEN_CHECKSUMS, ROOT) if golden else None,
         "note": "sum over all ranks' slabs of value[k] * w(global pair index k) mod 2^64 (+ the MinHash count histogram) against "
