@@ -1890,7 +1890,7 @@ extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offse
   };
   std::vector<Block> blk((size_t)blocks);
   cudaStream_t sc = nullptr, sd = nullptr;
-  cudaEvent_t ran = nullptr;
+  cudaEvent_t ran = nullptr, allocated = nullptr;
   int rc = DYNA_OK;
   auto cu = [&](cudaError_t e) {
     if (e != cudaSuccess && rc == DYNA_OK) rc = fail(DYNA_ERR_CUDA, "DynaAlign CUDA: dyna_nw_pair_stats8: %s", cudaGetErrorString(e));
@@ -1911,11 +1911,20 @@ extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offse
   cu(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
   cu(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
   cu(cudaEventCreateWithFlags(&ran, cudaEventDisableTiming));
+  cu(cudaEventCreateWithFlags(&allocated, cudaEventDisableTiming));
+  // DevBuf allocates in the order of the legacy stream; the two streams here do not synchronise with it, so every use of
+  // fresh memory on them is put behind an event recorded on the legacy stream after the allocation (a pool that has to
+  // map new memory does so in stream order: without this the copy engine read unmapped pages once the blocks were
+  // smaller than what the pool held cached -- an illegal access three blocks later)
+  auto after_alloc = [&](cudaStream_t s) {
+    cu(cudaEventRecord(allocated, cudaStreamLegacy));
+    cu(cudaStreamWaitEvent(s, allocated, 0));
+  };
   const int64_t first = tri_diag_rows(n, row_begin);
   for (int k = 0; k < blocks && rc == DYNA_OK; ++k) {
     const int64_t rb = bounds[(size_t)k], re = bounds[(size_t)k + 1];
     if (re <= rb) continue;
-    if (k >= 3) retire(blk[(size_t)k - 3]);
+    if (k >= 3 && !getenv("DYNA_NW_STATS8_KEEP")) retire(blk[(size_t)k - 3]);
     Block& b = blk[(size_t)k];
     b.plan = dyna_nw_plan_create(residues, offsets, n, matrix_name, gap_open, gap_ext, rb, re, g_device);
     if (!b.plan) { rc = plan_error_code(); break; }
@@ -1923,10 +1932,15 @@ extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offse
       rc = fail(DYNA_ERR_UNSUPPORTED, "dyna_nw_pair_stats8: alignment lengths up to %lld do not fit one byte", 2 * (long long)b.plan->max_cols);
       break;
     }
-    if ((rc = dyna_nw_plan_run(b.plan, sc)) != DYNA_OK) break;
+    after_alloc(sc);
+    if ((rc = dyna_nw_plan_run(b.plan, sc)) != DYNA_OK) {
+      if (getenv("DYNA_TIMING")) fprintf(stderr, "dyna_nw_pair_stats8: block %d of %d (rows %lld..%lld) failed\n", k, blocks, (long long)rb, (long long)re);
+      break;
+    }
     const int64_t bp = b.plan->pairs, at = tri_diag_rows(n, rb) - first;
     if (bp <= 0) continue;
     if (b.m8.alloc((size_t)bp) || b.l8.alloc((size_t)bp)) { rc = DYNA_ERR_CUDA; break; }
+    after_alloc(sd);
     cu(cudaEventRecord(ran, sc));
     cu(cudaStreamWaitEvent(sd, ran, 0));
     if ((rc = launch_nw_pack8(b.plan->matches.p, b.plan->length.p, bp, b.m8.p, b.l8.p, sd)) != DYNA_OK) break;
@@ -1940,6 +1954,7 @@ extern "C" int dyna_nw_pair_stats8(const uint8_t* residues, const int64_t* offse
   if (sd) cudaStreamSynchronize(sd);
   for (auto& b : blk) retire(b);
   if (ran) cudaEventDestroy(ran);
+  if (allocated) cudaEventDestroy(allocated);
   if (sc) cudaStreamDestroy(sc);
   if (sd) cudaStreamDestroy(sd);
   return rc;
