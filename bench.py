@@ -569,6 +569,13 @@ def phase_mh(ctx):
 
 
 # ================================================================== NW on the 100,000 peptides (north_star target), all ranks
+def safe_release(ctx):
+    try:
+        ctx.release_memory()
+    except Exception:  # a failed side measurement may have left the device in an error state: report, do not die here
+        pass
+
+
 def phase_mixed_nw(ctx, kind="mix"):
     """NW on inputs whose rows are not all alike.  "mix": a proteome-like length mix (log-normal, median 300 residues, a
     few sequences beyond 1024) -- what the planner makes of rows that do not sit next to a row of their own length.
@@ -818,22 +825,6 @@ def main():
     nw = phase_nw(ctx, ClockSampler(phys))
     n = nw["n"]
     mh = phase_mh(ctx)
-    try:
-        target = phase_target_nw(ctx)
-    except Exception as e:  # never let a side measurement take the headline line down
-        target = {"error": str(e)[:200]}
-        ctx.release_memory()
-    try:
-        mixed = phase_mixed_nw(ctx)
-    except Exception as e:
-        mixed = {"error": str(e)[:200]}
-        ctx.release_memory()
-    try:
-        longp = phase_mixed_nw(ctx, "long")
-    except Exception as e:
-        longp = {"error": str(e)[:200]}
-        ctx.release_memory()
-
     # ---------------- the R-facing call on all N GPUs of the box, from rank 0 (headline e2e)
     e2e_steps = max(1, min(args.steps, 3))
     inproc_s = inproc_similarity_nw(ctx, (nw["res"], nw["off"]), n, world, e2e_steps,
@@ -849,6 +840,23 @@ def main():
             cells2 = int((lens2 * np.cumsum(lens2[::-1])[::-1]).sum())
             inproc_c2 = {"n": len(h3), "n_gpus": world, "cells": cells2, "seconds": c2_s, "seconds_is": "median of 5 calls",
                          "gcups": cells2 / c2_s / 1e9}
+
+    # ---------------- side measurements, after the headline numbers are in (a failure here costs only its own entry)
+    try:
+        target = phase_target_nw(ctx)
+    except Exception as e:  # never let a side measurement take the headline line down
+        target = {"error": str(e)[:200]}
+        safe_release(ctx)
+    try:
+        mixed = phase_mixed_nw(ctx)
+    except Exception as e:
+        mixed = {"error": str(e)[:200]}
+        safe_release(ctx)
+    try:
+        longp = phase_mixed_nw(ctx, "long")
+    except Exception as e:
+        longp = {"error": str(e)[:200]}
+        safe_release(ctx)
 
     # ================================================================== CPU baseline (rank 0, N=1)
     cpu = None
@@ -869,7 +877,10 @@ def main():
     # ================================================================== BASELINE configs 1-3 through the drop-in API (rank 0)
     other = None
     if rank == 0:
-        other = small_configs(local_rank, with_cpu=(world == 1 and not args.skip_cpu))
+        try:
+            other = small_configs(local_rank, with_cpu=(world == 1 and not args.skip_cpu))
+        except Exception as e:  # e.g. the device left in an error state by a failed side measurement above
+            other = {"error": str(e)[:200]}
         if other is not None:
             other["target_nw_100k_peptides"] = target
             other["nw_mixed_lengths_3000"] = mixed
