@@ -350,6 +350,7 @@ extern "C" int dyna_mh_plan_upload_sequences(dyna_mh_plan* p, const uint8_t* res
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaStream_t prev = p->last_stream;
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   const int64_t total = offsets[p->n];
   p->max_len = 0;
   for (int64_t i = 0; i < p->n; ++i) p->max_len = std::max(p->max_len, offsets[i + 1] - offsets[i]);
@@ -371,6 +372,7 @@ extern "C" int dyna_mh_plan_upload_signatures(dyna_mh_plan* p, const uint32_t* s
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DYNA_CUDA(cudaMemcpyAsync(p->sig.p, sig, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyHostToDevice, st));
   int l = 0;
   DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l));
@@ -385,6 +387,7 @@ extern "C" int dyna_mh_plan_run_signatures(dyna_mh_plan* p, void* stream) {
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
   int l = 0;
   DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l));
@@ -404,6 +407,7 @@ extern "C" int dyna_mh_plan_run_signatures_shard(dyna_mh_plan* p, int code_row_b
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DYNA_TRY(launch_mh_signature_murmur3(p->res.p, p->off.p, p->n, p->max_len, p->k, p->seeds.p, p->n_hash, p->sig.p, st));
   int l = 0;
   DYNA_TRY(mh_plan_prepare_match_inputs(p, st, &l, code_row_begin, code_row_end));
@@ -422,6 +426,7 @@ extern "C" int dyna_mh_plan_run_match(dyna_mh_plan* p, void* stream) {
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   int l = 0;
   DYNA_TRY(mh_plan_ensure_counts(p));
   DYNA_TRY(launch_mh_match(p->sigT.p, p->npitch, p->hrows, p->n_hash, p->n, p->row_begin, p->row_end, p->counts.p,
@@ -448,6 +453,7 @@ extern "C" int dyna_mh_plan_run_match_sparse(dyna_mh_plan* p, int64_t max_incide
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   p->launches = 0;
   if (p->row_end <= p->row_begin || p->n < 2) {
     p->sp_runs = p->sp_incidences = 0;
@@ -527,6 +533,7 @@ extern "C" int dyna_mh_plan_fetch_signatures(dyna_mh_plan* p, uint32_t* sig_out,
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DYNA_CUDA(cudaMemcpyAsync(sig_out, p->sig.p, sizeof(uint32_t) * (size_t)p->n * p->n_hash, cudaMemcpyDeviceToHost, st));
   DYNA_CUDA(cudaStreamSynchronize(st));
   return DYNA_OK;
@@ -537,6 +544,7 @@ extern "C" int dyna_mh_plan_fetch_counts(dyna_mh_plan* p, uint16_t* counts_out, 
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DYNA_TRY(mh_plan_need_dense(p, st, "dyna_mh_plan_fetch_counts"));
   if (p->pairs > 0)
     DYNA_CUDA(cudaMemcpyAsync(counts_out, p->counts.p, sizeof(uint16_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
@@ -582,6 +590,7 @@ extern "C" int dyna_mh_plan_count_histogram(dyna_mh_plan* p, uint64_t* hist_out,
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DevBuf<unsigned long long> d_hist;
   DYNA_TRY(d_hist.alloc((size_t)p->n_hash + 1));
   const bool sparse = p->sparse_valid && !p->counts_valid;
@@ -637,6 +646,7 @@ extern "C" int dyna_mh_plan_threshold_edges(dyna_mh_plan* p, int min_count, int6
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   const int64_t rows = p->row_end - p->row_begin;
   if (n_edges_out) *n_edges_out = 0;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
@@ -707,6 +717,7 @@ extern "C" int dyna_mh_plan_run_match_fetch(dyna_mh_plan* p, uint16_t* counts_ou
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   const int64_t rows = p->row_end - p->row_begin;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
   DYNA_TRY(mh_plan_ensure_counts(p));
@@ -759,6 +770,7 @@ extern "C" int dyna_mh_plan_checksum(dyna_mh_plan* p, uint64_t* sum_out, void* s
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DevBuf<unsigned long long> d_sum;
   DYNA_TRY(d_sum.alloc(1));
   if (p->sparse_valid && !p->counts_valid) {
@@ -787,6 +799,7 @@ extern "C" int dyna_mh_plan_run_match_fetch8(dyna_mh_plan* p, uint8_t* counts8_o
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   if (n_esc_out) *n_esc_out = 0;
   const int64_t rows = p->row_end - p->row_begin;
   if (rows <= 0 || p->pairs <= 0) return DYNA_OK;
@@ -1273,6 +1286,7 @@ extern "C" int dyna_nw_plan_run(dyna_nw_plan* p, void* stream) {
   d.bias16 = p->bias16;
   p->launches = 0;
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   const bool fork = p->side[0] != nullptr;
   bool used[kNwSideStreams] = {false, false, false};
   if (fork) DYNA_CUDA(cudaEventRecord(p->ev_fork, st));
@@ -1330,6 +1344,7 @@ extern "C" int dyna_nw_plan_fetch(dyna_nw_plan* p, uint32_t* matches_out, uint32
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   if (p->pairs > 0) {
     DYNA_CUDA(cudaMemcpyAsync(matches_out, p->matches.p, sizeof(uint32_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
     DYNA_CUDA(cudaMemcpyAsync(length_out, p->length.p, sizeof(uint32_t) * (size_t)p->pairs, cudaMemcpyDeviceToHost, st));
@@ -1344,6 +1359,7 @@ extern "C" int dyna_nw_plan_checksum(dyna_nw_plan* p, uint64_t* sum_out, void* s
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DevBuf<unsigned long long> d_sum;
   DYNA_TRY(d_sum.alloc(2));
   const int64_t first = tri_diag_rows(p->n, p->row_begin);
@@ -1368,6 +1384,7 @@ extern "C" int dyna_nw_plan_fetch_packed8(dyna_nw_plan* p, uint8_t* matches8_out
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   if (p->pairs <= 0) return DYNA_OK;
   DevBuf<uint8_t> m8, l8;
   DYNA_TRY(m8.alloc((size_t)p->pairs));
@@ -1419,6 +1436,7 @@ extern "C" int dyna_nw_plan_stat_histogram(dyna_nw_plan* p, const int32_t* membe
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   const int64_t mdim = (int64_t)p->max_cols + 1, ldim = 2 * (int64_t)p->max_cols + 1;
   if (mdim * ldim > kNwHistMaxBins)
     return fail(DYNA_ERR_UNSUPPORTED, "dyna_nw_plan_stat_histogram: %lld x %lld (matches, length) bins exceed the supported %lld",
@@ -1443,6 +1461,7 @@ extern "C" int dyna_nw_plan_fetch_diagonal(dyna_nw_plan* p, const int32_t* membe
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   DevBuf<int32_t> d_members;
   NwNode nd;
   DYNA_TRY(nw_make_node(p, members, n_members, d_members, st, &nd, "dyna_nw_plan_fetch_diagonal"));
@@ -1504,6 +1523,7 @@ extern "C" int dyna_nw_plan_threshold_edges(dyna_nw_plan* p, const int32_t* memb
   DYNA_TRY(use_device(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->last_stream = st;
+  WorkStreamGuard work_stream_guard(st);
   if (n_edges_out) *n_edges_out = 0;
   DevBuf<int32_t> d_members;
   NwNode nd;

@@ -51,7 +51,8 @@ inline int fail(int code, const char* fmt, ...) {
 // one call are recycled by the next (clusterbreak invokes sim_fn once per recursion node; plain cudaMalloc/cudaFree of
 // the multi-GB result buffers was measured at up to 1 s per call).  All allocation and release is ordered on the
 // legacy default stream; the owners (plans, entry points) synchronise the stream their work ran on BEFORE releasing,
-// so a block handed to the next allocation is never still in use, whatever kind of stream the caller passed.
+// so a block handed to the next allocation is never still in use, whatever kind of stream the caller passed; the first
+// use of a fresh block on a non-blocking caller stream is ordered behind the allocation (WorkStreamGuard below).
 inline void dev_pool_keep_cached(int device) {
   static bool done[64] = {false};
   if (device < 0 || device >= 64 || done[device]) return;
@@ -61,6 +62,42 @@ inline void dev_pool_keep_cached(int device) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
   }
   done[device] = true;
+}
+
+// The stream the current entry point runs its work on (thread-local, set by WorkStreamGuard for the duration of the
+// call).  Allocation is ordered on the LEGACY stream; a blocking or NULL caller stream is ordered with it by definition,
+// a cudaStreamNonBlocking one is not -- a pool that has to map fresh memory does so in stream order, and work submitted to
+// an unrelated stream can reach the pages first.  For such a stream every DevBuf::alloc records an event on the legacy
+// stream behind the allocation and makes the work stream wait for it.  (Nothing changes for NULL / legacy callers.)
+inline cudaStream_t& work_stream_slot() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+struct WorkStreamGuard {
+  cudaStream_t prev;
+  explicit WorkStreamGuard(cudaStream_t st) : prev(work_stream_slot()) { work_stream_slot() = st; }
+  ~WorkStreamGuard() { work_stream_slot() = prev; }
+  WorkStreamGuard(const WorkStreamGuard&) = delete;
+  WorkStreamGuard& operator=(const WorkStreamGuard&) = delete;
+};
+inline void order_alloc_before_work_stream() {
+  cudaStream_t st = work_stream_slot();
+  if (st == nullptr || st == cudaStreamLegacy) return;
+  struct Ev {
+    cudaEvent_t ev = nullptr;
+    int dev = -1;
+    ~Ev() { if (ev) cudaEventDestroy(ev); }
+  };
+  static thread_local Ev e;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (!e.ev || e.dev != dev) {
+    if (e.ev) cudaEventDestroy(e.ev);
+    e.ev = nullptr;
+    if (cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming) != cudaSuccess) { e.ev = nullptr; return; }
+    e.dev = dev;
+  }
+  if (cudaEventRecord(e.ev, cudaStreamLegacy) == cudaSuccess) cudaStreamWaitEvent(st, e.ev, 0);
 }
 
 // RAII device buffer on the current device
@@ -77,6 +114,7 @@ struct DevBuf {
     n = count;
     if (count == 0) count = 1;
     DYNA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), 0));
+    order_alloc_before_work_stream();
     return DYNA_OK;
   }
   void release() {
