@@ -124,3 +124,21 @@ def test_long_rows_take_the_two_rows_multipass_kernel():
     for kind, r, row, row2, j0, cnt in k12:
         a, b = sorted((int(lens[row]), int(lens[row2])))
         assert 7 <= r <= 12 and (a - 1) // (32 * r) == (b - 1) // (32 * r), "both rows end in the same pass"
+
+
+def test_few_long_rows_go_back_to_the_one_row_multipass_kernel():
+    # the two-rows multi-pass kernel is used only when its rows hold a tenth of the plan's cells
+    rng = np.random.default_rng(10)
+    lens = np.concatenate([rng.integers(300, 360, size=600), rng.integers(800, 1000, size=6)])
+    rng.shuffle(lens)
+    units = check_cover(lens)
+    assert 12 not in set(units[:, 0]) and 6 in set(units[:, 0])
+
+
+def test_small_plans_get_narrow_two_rows_units():
+    lens = np.full(300, 330)
+    units = check_cover(lens)
+    k8 = units[units[:, 0] == 8]
+    assert len(k8) > 0 and k8[:, 5].max() <= 32      # 45,150 pairs: 32-column units
+    units = check_cover(np.full(1000, 330))
+    assert units[units[:, 0] == 8][:, 5].max() == 128   # 500,500 pairs: 128-column units
